@@ -1,0 +1,237 @@
+/* ellcuda.h — C ABI of libellcuda.so: the B200 (sm_100a) ellipsoid-update path.
+ *
+ * This header is the drop-in boundary.  The reference crate (luk036/ellalgo-rs v0.1.7)
+ * has no FFI of its own; its extension surface is the trait set
+ *   SearchSpace / UpdateByCutChoice            src/cutting_plane.rs:104-182
+ *   OracleFeas / OracleOptim / OracleOptimQ    src/cutting_plane.rs:119-147
+ * and the free drivers cutting_plane_feas/_optim/_optim_q (src/cutting_plane.rs:205-374).
+ * Every entry point below names the reference item a Rust shim would forward to it
+ * (INTEGRATION.md shows that shim).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *   - return 0 = ok; negative = infrastructure error (ELLCUDA_E_*), text via
+ *     ellcuda_last_error().  Algorithmic outcomes (CutStatus) travel only through
+ *     out-parameters.  The reference panics on shape errors (src/arr.rs:427-429); the
+ *     Rust shim turns ELLCUDA_E_ARG into panic!.
+ *   - all floating point is IEEE binary64, never contracted to FMA, sums in the
+ *     reference's left-to-right order (src/arr.rs:431-436, 446-450).
+ *   - there is NO CPU fallback: every compute call fails with ELLCUDA_E_CUDA when no
+ *     sm_100 device is usable.
+ *   - a handle is not thread-safe (the reference's `&mut self`); distinct handles are
+ *     independent.
+ */
+#ifndef ELLCUDA_H
+#define ELLCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes -------------------------------------------------------------------- */
+#define ELLCUDA_OK       0
+#define ELLCUDA_E_ARG   (-1) /* bad argument / shape (reference: assert! panic)            */
+#define ELLCUDA_E_CUDA  (-2) /* CUDA runtime error, or no usable sm_100 device             */
+#define ELLCUDA_E_COMM  (-3) /* multi-GPU exchange error                                   */
+#define ELLCUDA_E_OOM   (-4) /* device allocation failed                                   */
+
+/* ---- CutStatus, enum order of src/cutting_plane.rs:32-37 ------------------------------ */
+#define ELL_SUCCESS   0
+#define ELL_NOSOLN    1
+#define ELL_NOEFFECT  2
+#define ELL_UNKNOWN   3
+
+/* ---- why a cutting_plane_* run stopped.  The reference returns only (Option<x>, niter);
+ *      north_star asks for the termination status too, so the batch API exports it.
+ *      1,2 reuse the CutStatus codes.                                                      */
+#define ELL_EXIT_NOSOLN    1 /* update returned NoSoln   (src/cutting_plane.rs:222,308,358) */
+#define ELL_EXIT_NOEFFECT  2 /* update returned NoEffect (…:222,308; optim_q :361-364)      */
+#define ELL_EXIT_TOL       4 /* Success but tsq < tolerance (…:222,308,369)                 */
+#define ELL_EXIT_MAXIT     5 /* loop ran out (…:226,312,373)                                */
+#define ELL_EXIT_FEASIBLE  6 /* cutting_plane_feas: oracle returned None (…:217-219)        */
+
+/* ---- search-space kind ---------------------------------------------------------------- */
+#define ELL_KIND_ELL        0 /* src/ell.rs        */
+#define ELL_KIND_ELLSTABLE  1 /* src/ell_stable.rs */
+
+/* ---- which SearchSpace method — src/cutting_plane.rs:161-180 -------------------------- */
+#define ELL_UPDATE_BIAS     0 /* update_bias_cut    */
+#define ELL_UPDATE_CENTRAL  1 /* update_central_cut */
+#define ELL_UPDATE_Q        2 /* update_q           */
+
+/* ---- driver ---------------------------------------------------------------------------- */
+#define ELL_MODE_OPTIM    0 /* cutting_plane_optim   src/cutting_plane.rs:286-313 */
+#define ELL_MODE_FEAS     1 /* cutting_plane_feas    src/cutting_plane.rs:205-227 */
+#define ELL_MODE_OPTIM_Q  2 /* cutting_plane_optim_q src/cutting_plane.rs:331-374 */
+
+/* ---- built-in device oracles (the reference's own oracle structs, restated on device) -- */
+#define ELL_ORACLE_EXAMPLE1     0 /* src/example1.rs:8-30            optim n=2  no params   */
+#define ELL_ORACLE_EXAMPLE1_RR  1 /* src/example1_rr.rs:13-53        optim n=2  no params   */
+#define ELL_ORACLE_EXAMPLE4     2 /* src/example4.rs:10-57           optim n=2  no params   */
+#define ELL_ORACLE_QUASICVX     3 /* src/quasicvx.rs:11-51           optim n=2  no params   */
+#define ELL_ORACLE_PROFIT       4 /* src/oracles/profit_oracle.rs:42-114  optim n=2
+                                     params[7] = p, A, k, a0, a1, v0, v1                    */
+#define ELL_ORACLE_PROFIT_RB    5 /* …:116-161  params[12] = the 7 above + e1..e5           */
+#define ELL_ORACLE_PROFIT_Q     6 /* …:163-198  optim_q, params[7]                          */
+#define ELL_ORACLE_LOWPASS      7 /* src/oracles/lowpass_oracle.rs:7-150  optim, n taps
+                                     params[5] = wpass, wstop, lp_sq, up_sq, sp_sq
+                                     table = spectrum, aux[0] = mdim rows × n (see
+                                     ellcuda_lowpass_table)                                 */
+#define ELL_ORACLE_BOWL         8 /* tests/integration_test.rs:90-105 optim, any n
+                                     params[n] = target                                     */
+#define ELL_ORACLE_LMI          9 /* src/oracles/lmi_oracle.rs:5-45 + ldlt_mgr.rs  feas
+                                     table = F_0..F_{n-1} (each m×m row-major) then B (m×m);
+                                     aux[0] = m                                             */
+#define ELL_ORACLE_EXAMPLE2    10 /* tests/example2_tests.rs:12-48   feas  n=2              */
+#define ELL_ORACLE_EXAMPLE3    11 /* src/example3.rs:10-60           feas  n=2 params[1]=target */
+#define ELL_ORACLE_HALFPLANE   12 /* tests/cutting_plane_tests.rs:12-28  feas n=2           */
+#define ELL_ORACLE_ALWAYS_CUT  13 /* tests/cutting_plane_tests.rs:33-42, 91-99  feas|optim  */
+#define ELL_ORACLE_OPTIM_BOX   14 /* tests/cutting_plane_tests.rs:47-73  optim n=2          */
+#define ELL_ORACLE_LMI_LINOPT  15 /* tests/lmi_tests.rs:121-172 MyLmiOracle: min c·x over L
+                                     LMI blocks, round-robin.  table = c[n], then per block
+                                     F_0..F_{n-1}, B;  aux[0] = L, aux[1..L] = block sizes  */
+#define ELL_ORACLE_COUNT       16
+
+/* ======================================================================================= *
+ *  Batched mode: `count` independent problems, the whole cutting-plane loop on-device.
+ *  Replaces, per problem i:
+ *      let mut space = Ell::new_with_matrix(kappa0[i], mq0 | diag(diag0[i]) | I, xc0[i]);
+ *      let mut omega = <Oracle>::new(params[i], table);
+ *      let (xbest, num_iters) = cutting_plane_{optim,feas,optim_q}(&mut omega, &mut space,
+ *                                   &mut gamma[i], &Options{max_iters, tolerance});
+ *  (src/ell.rs:31-78, src/ell_stable.rs:18-35, src/cutting_plane.rs:50-100, 205-374).
+ *
+ *  Per-instance arrays are SoA with an explicit stride in doubles between instances;
+ *  stride 0 means one value shared by every instance.
+ * ======================================================================================= */
+typedef struct ell_batch_desc {
+    int32_t kind;             /* ELL_KIND_*                                               */
+    int32_t oracle_id;        /* ELL_ORACLE_*                                             */
+    int32_t mode;             /* ELL_MODE_*                                               */
+    int32_t n;                /* dimension of xc                                          */
+    int64_t count;            /* number of independent problems                           */
+    int64_t max_iters;        /* Options::max_iters  (default 2000, …:97-99)              */
+    double  tolerance;        /* Options::tolerance  (default 1e-20)                      */
+    int32_t no_defer_trick;   /* Ell::no_defer_trick  src/ell.rs:10,132-135               */
+    int32_t use_parallel_cut; /* EllCalc::use_parallel_cut src/ell_calc.rs:630 (default 1) */
+
+    const double* kappa0;  int64_t kappa0_stride;  /* 1 value / instance                  */
+    const double* xc0;     int64_t xc0_stride;     /* n values / instance                 */
+    const double* diag0;   int64_t diag0_stride;   /* n values; NULL ⇒ identity           */
+    const double* mq0;     int64_t mq0_stride;     /* n·n values row-major; NULL ⇒ diag0  */
+    const double* gamma0;  int64_t gamma0_stride;  /* 1 value; ignored in FEAS mode       */
+    const double* params;  int64_t params_stride;  /* params_width values / instance      */
+    int32_t params_width;
+    int32_t _pad0;
+    const double* table;   int64_t table_len;      /* shared read-only table (doubles)    */
+    int32_t aux[8];           /* oracle-specific integers, see ELL_ORACLE_*               */
+
+    int32_t device;           /* CUDA device ordinal                                      */
+    int32_t on_device;        /* 0: every pointer is host memory (copied in/out inside the
+                                    call); 1: every pointer is device memory on `device`   */
+    void*   stream;           /* cudaStream_t to run on, NULL ⇒ the library's own stream   */
+} ell_batch_desc;
+
+typedef struct ell_batch_result { /* caller-allocated; optional members may be NULL       */
+    double*  xbest;       /* count·n  Option<xbest> payload (unchanged where has_xbest=0)  */
+    uint8_t* has_xbest;   /* count    1 = Some                                             */
+    int64_t* num_iters;   /* count    second tuple member of the driver's return value     */
+    int32_t* exit_status; /* count    ELL_EXIT_*                                           */
+    double*  gamma;       /* count    final gamma (optim modes), optional                  */
+    double*  tsq;         /* count    final space.tsq(), optional                          */
+    double*  xc;          /* count·n  final space.xc(),  optional                          */
+    double*  kappa;       /* count    final kappa,       optional                          */
+} ell_batch_result;
+
+/* Runs the batch on desc->device.  Synchronous when on_device==0; when on_device==1 the
+ * work is enqueued on desc->stream and the call returns without synchronising.          */
+int ellcuda_batch_solve(const ell_batch_desc* desc, const ell_batch_result* res);
+
+/* Number of kernels the last ellcuda_batch_solve on this thread launched (bench counter). */
+int64_t ellcuda_last_launch_count(void);
+
+/* LowpassOracle::new's spectrum table (src/oracles/lowpass_oracle.rs:24-33 with
+ * linspace src/arr.rs:506-520): out[i*n+j], i < 15·n.  Host-side, glibc cos, so the table
+ * the device reads is bit-identical to the one the Rust constructor builds.             */
+int ellcuda_lowpass_table(int32_t n, double* out_mdim_by_n);
+/* nwpass / nwstop of LowpassOracle::new (…:35-36). */
+int32_t ellcuda_lowpass_band_edge(int32_t n, double w);
+
+/* ======================================================================================= *
+ *  Single-instance mode (large n): an `Ell` whose matrix lives in HBM.
+ *  The handle stands for one `Ell` value (src/ell.rs:9-16).  With row sharding
+ *  (row_begin,row_end) it stands for one rank's slab of rows; ranks exchange the slab
+ *  results of `grad_t` between ellcuda_update_begin and ellcuda_update_finish.
+ * ======================================================================================= */
+typedef struct ellcuda_ctx* ell_handle;
+
+typedef struct ell_create_desc {
+    int32_t kind;              /* ELL_KIND_ELL (ELLSTABLE has no large-n form: its
+                                  triangular recurrences do not shard, use batched mode)  */
+    int32_t device;
+    int64_t n;
+    double  kappa;             /* Ell::new_with_scalar(kappa,…) / new_with_matrix(kappa,…) */
+    const double* mq;          /* host, n·n row-major, symmetric; NULL ⇒ diag             */
+    const double* diag;        /* host, n; NULL ⇒ identity   (Ell::new: kappa=1, diag=val) */
+    const double* xc;          /* host, n                                                 */
+    int32_t no_defer_trick;
+    int32_t use_parallel_cut;
+    int64_t row_begin, row_end;/* this handle's slab of rows; 0,n for a whole matrix       */
+    int32_t reduce_mode;       /* 0: reference order (bit-identical grad_t and omega);
+                                  k>0: each row sum split into k ordered segments and omega
+                                  reduced blockwise — deterministic, ≤1e-13 rel. of mode 0 */
+    int32_t _pad0;
+    void*   stream;            /* cudaStream_t, NULL ⇒ own stream                          */
+} ell_create_desc;
+
+int  ellcuda_create(const ell_create_desc* desc, ell_handle* out); /* Ell::new* src/ell.rs:31-78 */
+int  ellcuda_clone(ell_handle h, ell_handle* out);                 /* #[derive(Clone)] src/ell.rs:8 */
+void ellcuda_destroy(ell_handle h);                                /* Drop                     */
+
+int ellcuda_xc(ell_handle h, double* out_n);              /* SearchSpace::xc   src/ell.rs:144-146 */
+int ellcuda_set_xc(ell_handle h, const double* x_n);      /* SearchSpace::set_xc      …:177-179   */
+int ellcuda_tsq(ell_handle h, double* out);               /* SearchSpace::tsq         …:149-151   */
+int ellcuda_kappa(ell_handle h, double* out);             /* pub field Ell::kappa     …:13        */
+int ellcuda_get_mq(ell_handle h, double* out_rows_by_n);  /* pub field Ell::mq (this slab's rows,
+                                                             pending rank-1 applied first)        */
+
+/* SearchSpace::update_{bias_cut,central_cut,q} with SingleCut(beta0) [has_beta1 = -1],
+ * ParallelCut(beta0, None) [0] or ParallelCut(beta0, Some(beta1)) [1]
+ * (src/ell.rs:153-175, 182-229 → update_core :97-137).  `grad` is host memory, n values.
+ * Whole-matrix handles only.  Synchronous: *out_status is valid on return.               */
+int ellcuda_update(ell_handle h, int32_t which, const double* grad_host,
+                   double beta0, int32_t has_beta1, double beta1, int32_t* out_status);
+
+/* Same, split for sharded / device-resident use.  `grad_dev` is device memory (n values).
+ *   begin : applies the previous cut's deferred rank-1 to this slab and, in the same sweep
+ *           over M, forms this slab's part of grad_t = M·grad   (ell.rs:102, 117-128)
+ *   (exchange: every rank needs all n entries of grad_t — allgather of
+ *    ellcuda_grad_t_ptr(h)[row_begin..row_end] in place; nothing to do for a whole matrix)
+ *   finish: omega, tsq, EllCalc, xc, kappa (ell.rs:103-115,130-135), identically on every
+ *           rank; the CutStatus is left in device memory (ellcuda_status_ptr) so that the
+ *           sequence can be captured in a CUDA graph.                                      */
+int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev,
+                         double beta0, int32_t has_beta1, double beta1);
+int ellcuda_update_finish(ell_handle h);
+double*  ellcuda_grad_t_ptr(ell_handle h);   /* device, n doubles                          */
+int32_t* ellcuda_status_ptr(ell_handle h);   /* device, CutStatus of the last finish       */
+int ellcuda_last_status(ell_handle h, int32_t* out_status); /* synchronises, reads status   */
+int ellcuda_set_stream(ell_handle h, void* stream);
+int ellcuda_sync(ell_handle h);
+/* duration in ms of the most recent M sweep on this handle (CUDA events on its stream);
+ * negative if none was timed.  ellcuda_set_timing(h,1) enables event recording.           */
+int ellcuda_set_timing(ell_handle h, int32_t on);
+float ellcuda_last_sweep_ms(ell_handle h);
+int64_t ellcuda_handle_launch_count(ell_handle h);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+const char* ellcuda_last_error(void);   /* thread-local, never NULL                          */
+int ellcuda_version(void);              /* 100*major + minor                                 */
+int ellcuda_device_count(void);         /* usable sm_100 devices (0 ⇒ every compute call fails) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELLCUDA_H */
