@@ -1,0 +1,58 @@
+// common.cuh — kernel argument records and small helpers shared by the .cu files of libellcuda.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/ellcuda.h"
+#include "ell_calc.cuh"
+
+namespace ellcuda {
+
+// Device-side picture of ell_batch_desc + ell_batch_result (all pointers are device pointers).
+struct BatchArgs {
+    int n;
+    int mode;
+    int kind;
+    int no_defer_trick;
+    int use_parallel_cut;
+    int params_width;
+    long long count;
+    long long max_iters;
+    double tolerance;
+    const double* kappa0; long long kappa0_stride;
+    const double* xc0;    long long xc0_stride;
+    const double* diag0;  long long diag0_stride;
+    const double* mq0;    long long mq0_stride;
+    const double* gamma0; long long gamma0_stride;
+    const double* params; long long params_stride;
+    const double* table;  long long table_len;
+    int aux[8];
+    // results (may be null except num_iters / exit_status which the host always provides)
+    double* xbest;
+    unsigned char* has_xbest;
+    long long* num_iters;
+    int* exit_status;
+    double* gamma;
+    double* tsq;
+    double* xc;
+    double* kappa;
+    unsigned long long* queue;  // dynamic work counter (persistent kernels)
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define ELL_CUDA_TRY(expr)                                                         \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) return ::ellcuda::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// launchers implemented per kernel family; each returns ELLCUDA_* and adds to *launches
+int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
+int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
+int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
+
+}  // namespace ellcuda

@@ -1,0 +1,173 @@
+"""GPU parity tests, batched mode: the CUDA path (through the C ABI, ellcuda_batch_solve) against the CPU checker
+on the same seeded inputs."""
+import math
+
+import numpy as np
+import pytest
+
+from ellalgo_rs_b200 import _abi as A
+from ellalgo_rs_b200 import batch
+from ellalgo_rs_b200 import workloads as W
+from ellalgo_rs_b200.problem import BatchProblem
+from parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def both(ref, prob):
+    return batch.solve_batch(prob), ref.solve(prob)
+
+
+# ------------------------------------------------------------------ n = 2, thread per problem
+def test_example1_pinned(ref):  # src/example1.rs:39-50
+    g, r = both(ref, W.example1())
+    assert g.num_iters[0] == 25 and g.exit_status[0] == A.EXIT_TOL and g.has_xbest[0] == 1
+    assert_parity(g, r, exact=True, what="example1")
+
+
+FIXTURES_N2 = [
+    ("example1_rr", dict(oracle_id=A.ORACLE_EXAMPLE1_RR, kappa0=10.0, gamma0=-math.inf, tolerance=1e-10), 25),
+    ("example4", dict(oracle_id=A.ORACLE_EXAMPLE4, kappa0=10.0, gamma0=-math.inf, tolerance=1e-10), 82),
+    ("example1_infeasible1", dict(oracle_id=A.ORACLE_EXAMPLE1, kappa0=1.0, diag0=[10.0, 10.0], xc0=[100.0, 100.0], gamma0=-math.inf), None),
+    ("example1_infeasible2", dict(oracle_id=A.ORACLE_EXAMPLE1, kappa0=1.0, diag0=[10.0, 10.0], gamma0=100.0), None),
+    ("halfplane", dict(oracle_id=A.ORACLE_HALFPLANE, mode=A.MODE_FEAS, kappa0=10.0, max_iters=200), 0),
+    ("always_cut_feas", dict(oracle_id=A.ORACLE_ALWAYS_CUT, mode=A.MODE_FEAS, kappa0=10.0, max_iters=200), 2),
+    ("always_cut_feas5", dict(oracle_id=A.ORACLE_ALWAYS_CUT, mode=A.MODE_FEAS, kappa0=10.0, max_iters=5), 2),
+    ("always_cut_optim", dict(oracle_id=A.ORACLE_ALWAYS_CUT, kappa0=10.0, gamma0=0.0, max_iters=5), 2),
+    ("always_cut_q", dict(oracle_id=A.ORACLE_ALWAYS_CUT, mode=A.MODE_OPTIM_Q, kappa0=10.0, gamma0=0.0, max_iters=5), 2),
+    ("optim_box", dict(oracle_id=A.ORACLE_OPTIM_BOX, kappa0=10.0, gamma0=0.0, max_iters=200), None),
+    ("optim_box_nosoln", dict(oracle_id=A.ORACLE_OPTIM_BOX, kappa0=10.0, gamma0=100.0, max_iters=4), 0),
+    ("optim_box_q", dict(oracle_id=A.ORACLE_OPTIM_BOX, mode=A.MODE_OPTIM_Q, kappa0=10.0, gamma0=0.0, max_iters=200), None),
+    ("optim_box_q_nosoln", dict(oracle_id=A.ORACLE_OPTIM_BOX, mode=A.MODE_OPTIM_Q, kappa0=10.0, gamma0=100.0, max_iters=20), 0),
+    ("example2", dict(oracle_id=A.ORACLE_EXAMPLE2, mode=A.MODE_FEAS, kappa0=10.0), 1),
+    ("example2_inf", dict(oracle_id=A.ORACLE_EXAMPLE2, mode=A.MODE_FEAS, kappa0=10.0, xc0=[100.0, 100.0]), 0),
+    ("example3", dict(oracle_id=A.ORACLE_EXAMPLE3, mode=A.MODE_FEAS, kappa0=100.0, params=[-20.0], tolerance=1e-8), None),
+    ("max_iters_0", dict(oracle_id=A.ORACLE_EXAMPLE1, kappa0=10.0, gamma0=-math.inf, max_iters=0), 0),
+]
+
+
+@pytest.mark.parametrize("name,kw,pinned", FIXTURES_N2, ids=[f[0] for f in FIXTURES_N2])
+@pytest.mark.parametrize("kind", [A.KIND_ELL, A.KIND_ELLSTABLE])
+def test_fixtures_n2(ref, name, kw, pinned, kind):
+    prob = BatchProblem(n=2, count=3, kind=kind, **kw)  # 3 identical copies: also exercises the partial warp
+    g, r = both(ref, prob)
+    if pinned is not None and kind == A.KIND_ELL:
+        assert (g.num_iters == pinned).all(), f"{name}: {g.num_iters} != pinned {pinned}"
+    assert_parity(g, r, exact=True, what=name)
+
+
+@pytest.mark.parametrize("kind", [A.KIND_ELL, A.KIND_ELLSTABLE])
+def test_quasicvx(ref, kind):  # src/quasicvx.rs:61-131 (exp on device vs glibc: tolerance, not bits)
+    prob = BatchProblem(oracle_id=A.ORACLE_QUASICVX, n=2, count=1, kind=kind, kappa0=1.0, diag0=[10.0, 10.0], gamma0=0.0,
+                        tolerance=1e-8)
+    g, r = both(ref, prob)
+    if kind == A.KIND_ELL:
+        assert g.num_iters[0] == 35
+    assert_parity(g, r, exact=False, what="quasicvx")
+
+
+def test_profit_pinned_and_random(ref):  # src/oracles/profit_oracle.rs:207-223 + C2 generator
+    prob = W.profit(20000)
+    g, r = both(ref, prob)
+    assert g.num_iters[0] == 83 and g.xbest[0, 0] <= math.log(30.5)
+    assert_parity(g, r, exact=False, what="profit")
+
+
+def test_profit_rb_and_q(ref):  # :225-260
+    p = W.profit(1)
+    p.oracle_id = A.ORACLE_PROFIT_RB
+    p.params = np.concatenate([W.PROFIT_REF, [0.003, 0.007, 1.0, 1.0, 1.0]])
+    g, r = both(ref, p)
+    assert g.num_iters[0] == 90
+    assert_parity(g, r, exact=False, what="profit_rb")
+    p = W.profit(4096)
+    p.oracle_id, p.mode = A.ORACLE_PROFIT_Q, A.MODE_OPTIM_Q
+    g, r = both(ref, p)
+    assert g.num_iters[0] == 29
+    assert_parity(g, r, exact=False, what="profit_q")
+
+
+def test_flags_n2(ref):
+    for kw in (dict(no_defer_trick=True), dict(use_parallel_cut=False)):
+        prob = BatchProblem(oracle_id=A.ORACLE_EXAMPLE4, n=2, count=2, kappa0=10.0, gamma0=-math.inf, tolerance=1e-10, **kw)
+        g, r = both(ref, prob)
+        assert_parity(g, r, exact=True, what=str(kw))
+
+
+# ------------------------------------------------------------------ 3 <= n <= 32, warp per problem
+@pytest.mark.parametrize("n,count,spread", [(32, 300, 1.0), (32, 64, 3.0), (5, 33, 2.0), (17, 40, 1.0), (3, 7, 1.0)])
+def test_bowl(ref, n, count, spread):  # tests/integration_test.rs:90-105 — no libm: bit-identical
+    prob = W.bowl(count, n=n, spread=spread, max_iters=20000)
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"bowl n={n}")
+
+
+def test_bowl_reference_case(ref):  # tests/integration_test.rs:107-131: n=5, target 1..5, kappa 10
+    prob = BatchProblem(oracle_id=A.ORACLE_BOWL, n=5, count=1, kappa0=10.0, gamma0=math.inf, params=[1.0, 2, 3, 4, 5],
+                        max_iters=2000, tolerance=1e-10)
+    g, r = both(ref, prob)
+    assert g.has_xbest[0] == 1 and math.sqrt(((g.xbest[0] - np.arange(1, 6)) ** 2).mean()) < 3.0
+    assert_parity(g, r, exact=True, what="HighDimOracle")
+
+
+def test_bowl_flags(ref):
+    for kw in (dict(no_defer_trick=True), dict(max_iters=2000), dict(max_iters=1)):
+        prob = W.bowl(16, n=32, **({"max_iters": 500} | kw))
+        prob.no_defer_trick = kw.get("no_defer_trick", False)
+        g, r = both(ref, prob)
+        assert_parity(g, r, exact=True, what=str(kw))
+
+
+def test_bowl_matrix_start(ref):  # Ell::new (diag) and new_with_matrix (symmetric dense) starts
+    n, count = 32, 8
+    rng = np.random.default_rng(7)
+    prob = W.bowl(count, n=n, max_iters=300)
+    prob.kappa0 = np.array([1.0])
+    prob.diag0 = rng.uniform(50.0, 150.0, size=(count, n))
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what="diag start")
+    a = rng.uniform(-1, 1, size=(n, n))
+    prob = W.bowl(count, n=n, max_iters=300)
+    prob.kappa0 = np.array([1.0])
+    prob.mq0 = 100.0 * np.eye(n) + (a + a.T)
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what="matrix start")
+
+
+def test_lowpass(ref):  # src/oracles/lowpass_oracle.rs — table built with glibc cos on the host: bit-identical
+    t = batch.lowpass_table(32)
+    assert np.array_equal(t, ref.lowpass_table(32))
+    prob = W.lowpass(12, t)
+    g, r = both(ref, prob)
+    assert g.num_iters[0] == 12481 and g.exit_status[0] == A.EXIT_TOL  # survey-derived canonical instance
+    assert_parity(g, r, exact=True, what="lowpass n=32")
+
+
+def test_lowpass_literal_case(ref):  # create_lowpass_case(32) is degenerate: NoSoln at iteration 0
+    t = batch.lowpass_table(32)
+    prob = W.lowpass(1, t)
+    prob.params = ref.lowpass_case_params()
+    prob.gamma0 = np.array([prob.params[4]])
+    g, r = both(ref, prob)
+    assert (g.num_iters[0], g.exit_status[0], g.has_xbest[0]) == (0, A.EXIT_NOSOLN, 0)
+    assert_parity(g, r, exact=True, what="lowpass literal")
+
+
+@pytest.mark.parametrize("n", [8, 15])
+def test_lowpass_small_n(ref, n):
+    t = batch.lowpass_table(n)
+    prob = W.lowpass(5, t, n=n, max_iters=5000)
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"lowpass n={n}")
+
+
+def test_empty_batch_and_bad_args(ref):
+    out = batch.solve_batch(W.bowl(0, n=32))
+    assert out.num_iters.size == 0
+    from ellalgo_rs_b200._lib import EllCudaError
+    with pytest.raises(EllCudaError):
+        batch.solve_batch(BatchProblem(oracle_id=A.ORACLE_PROFIT, n=3, count=1, params=W.PROFIT_REF))
+    bad = W.bowl(2, n=4)
+    bad.mq0 = np.arange(16.0).reshape(4, 4)
+    with pytest.raises(EllCudaError):
+        batch.solve_batch(bad)
