@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on B200: "ellipsoid iterations/sec (batched n=32) and Ell::update HBM GB/s at
+n=16384".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                            the reference algorithm's CPU path (oracle port)
+
+One JSON line on rank 0.  Headline workload (configs[2]): LowpassOracle n=32, 65536 independent problems per GPU,
+Ell::new_with_scalar(40, 0), Options{50000, 1e-14}; a step = one ellcuda_batch_solve over the batch; the unit is one
+ellipsoid iteration = one update_core call (oracle evaluation included in the time).  `large_n` carries the second
+half of the metric (configs[4]): one n=16384 ellipsoid, ParallelCut(0.01, Some(0.10)) via update_bias_cut, 200
+updates after 20 warm-up, row-sharded over the N ranks with an NCCL allgather of grad_t per update.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TAPS = 32
+PER_GPU = 65536
+LARGE_N = 16384
+LARGE_UPDATES, LARGE_WARMUP = 200, 20
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def iterations_done(num_iters, exit_status):
+    """update_core calls performed: the terminating iteration ran an update too (src/cutting_plane.rs:299-311)"""
+    return int(num_iters.sum()) + int((exit_status != 5).sum())
+
+
+# ================================================================================================== reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ellref_py as R
+    from ellalgo_rs_b200 import workloads as W
+    T = R.hardware_threads()
+    table = R.lowpass_table(N_TAPS)
+    sample = max(16 * T, 32)
+    prob = W.lowpass(sample, table, n=N_TAPS)
+    for _ in range(args.warmup):
+        R.solve(W.lowpass(max(T // 2, 1), table, n=N_TAPS), T)
+    t_tot, it_tot = 0.0, 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        o = R.solve(prob, T)
+        t_tot += time.perf_counter() - t0
+        it_tot += iterations_done(o.num_iters, o.exit_status)
+    val = it_tot / t_tot
+    desc = f"first {sample} instances of the lowpass n=32 batch per step, {T} std::threads over instances"
+    line = {
+        "impl": "reference", "metric": "ellipsoid iterations/sec (batched n=32)", "value": val, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": T, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the Rust reference cannot be built in this image (no cargo/rustc); this is oracle/ — a line-by-line C++ "
+                "restatement pinned to the reference's own iteration counts — on the box's host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(gpus):
+    return {"workload": "configs[2]: LowpassOracle n=32 (spectrum 480x32), 65536 independent problems per GPU, "
+                        "Ell::new_with_scalar(40,0), Options{max_iters 50000, tol 1e-14}, cutting_plane_optim on-device",
+            "problems_per_gpu": PER_GPU, "n": N_TAPS, "parallelism": f"problems sharded over {gpus} GPU(s), no collective",
+            "l2": "L2 flushed (512 MiB memset) between timed steps; large_n streams a 2 GiB matrix (> L2)"}
+
+
+# ================================================================================================== our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-large-n", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--per-gpu", type=int, default=PER_GPU)
+    ap.add_argument("--large-n", type=int, default=LARGE_N)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ellalgo_rs_b200 import _abi as A
+    from ellalgo_rs_b200 import batch
+    from ellalgo_rs_b200 import workloads as W
+    from ellalgo_rs_b200._lib import check, lib
+    from ellalgo_rs_b200.cutting_plane import ParallelCut
+    from ellalgo_rs_b200.parallel import ShardedEll
+    from ellalgo_rs_b200.problem import BatchProblem
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    L = lib()
+    peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    # ---------------------------------------------------------------- batched lowpass n=32 (headline)
+    cnt = args.per_gpu
+    table = batch.lowpass_table(N_TAPS)
+    host = W.lowpass(cnt, table, n=N_TAPS, first=rank * cnt)   # weak scaling: rank r owns global problems [r·cnt, (r+1)·cnt)
+    host.device = local
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+
+    pinned = {k: pin(getattr(host, k)) for k in ("kappa0", "xc0", "gamma0", "params", "table")}
+    devin = {k: v.to(dev) for k, v in pinned.items()}
+    dprob = BatchProblem(oracle_id=A.ORACLE_LOWPASS, n=N_TAPS, count=cnt, kappa0=devin["kappa0"], xc0=devin["xc0"],
+                         gamma0=devin["gamma0"], params=devin["params"], table=devin["table"], aux=[15 * N_TAPS],
+                         max_iters=host.max_iters, tolerance=host.tolerance, device=local)
+    dres = {"xbest": torch.zeros(cnt, N_TAPS, dtype=torch.float64, device=dev),
+            "has_xbest": torch.zeros(cnt, dtype=torch.uint8, device=dev),
+            "num_iters": torch.zeros(cnt, dtype=torch.int64, device=dev),
+            "exit_status": torch.zeros(cnt, dtype=torch.int32, device=dev),
+            "gamma": torch.zeros(cnt, dtype=torch.float64, device=dev)}
+
+    launches = 0
+    for _ in range(args.warmup):
+        batch.solve_batch_device(dprob, dres, sptr)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush_buf.zero_()
+        ev[k][0].record(stream)
+        launches += batch.solve_batch_device(dprob, dres, sptr)
+        ev[k][1].record(stream)
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = max_over_ranks(sum(step_ms) / 1e3)
+    iters_step = iterations_done(dres["num_iters"].cpu().numpy(), dres["exit_status"].cpu().numpy())
+    iters_all = sum_over_ranks(float(iters_step)) * args.steps
+    value = iters_all / t_dev
+    kern_ms = float(np.mean(step_ms))  # one launch per step: the step IS the kernel
+
+    # e2e: host (pinned) buffers through the public C-ABI call, H2D + kernel + D2H inside the timed region
+    hprob = BatchProblem(oracle_id=A.ORACLE_LOWPASS, n=N_TAPS, count=cnt, kappa0=pinned["kappa0"].numpy(),
+                         xc0=pinned["xc0"].numpy(), gamma0=pinned["gamma0"].numpy(), params=pinned["params"].numpy(),
+                         table=pinned["table"].numpy(), aux=[15 * N_TAPS], max_iters=host.max_iters,
+                         tolerance=host.tolerance, device=local)
+    hres_t = {"xbest": torch.zeros(cnt, N_TAPS, dtype=torch.float64).pin_memory(),
+              "has_xbest": torch.zeros(cnt, dtype=torch.uint8).pin_memory(),
+              "num_iters": torch.zeros(cnt, dtype=torch.int64).pin_memory(),
+              "exit_status": torch.zeros(cnt, dtype=torch.int32).pin_memory(),
+              "gamma": torch.zeros(cnt, dtype=torch.float64).pin_memory()}
+    hd = hprob.to_desc(sptr)
+    hr = A.BatchResult()
+    for k, t in hres_t.items():
+        setattr(hr, k, t.data_ptr())
+    h2d = sum(int(pinned[k].numel()) * 8 for k in pinned)
+    d2h = sum(int(t.numel()) * t.element_size() for t in hres_t.values())
+    check(L.ellcuda_batch_solve(C.byref(hd), C.byref(hr)))  # warm
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e2e = 0.0
+    for k in range(args.steps):
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        check(L.ellcuda_batch_solve(C.byref(hd), C.byref(hr)))
+        e1.record(stream)
+        e1.synchronize()
+        t_e2e += e0.elapsed_time(e1) / 1e3
+    barrier()
+    t_e2e = max_over_ranks(t_e2e)
+    e2e_iters = sum_over_ranks(float(iterations_done(hres_t["num_iters"].numpy(), hres_t["exit_status"].numpy()))) * args.steps
+    e2e_value = e2e_iters / t_e2e
+    clocks = sampler.stop() if sampler else None
+
+    # ---------------------------------------------------------------- large n (second half of the metric)
+    large = None
+    if not args.skip_large_n:
+        n = args.large_n
+        mode = 0 if world == 1 else 8
+        ell = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local)
+        grads = [torch.from_numpy(W.large_n_grad(n, k)).to(dev) for k in range(16)]
+        cut = ParallelCut(*W.LARGE_N_CUT)
+        for k in range(LARGE_WARMUP):
+            ell.update_async(A.UPDATE_BIAS, grads[k % 16], cut)
+        barrier()
+        ell.ell.set_timing(True)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ell.ell.launches
+        sweeps = []
+        a0.record(stream)
+        for k in range(LARGE_UPDATES):
+            ell.update_async(A.UPDATE_BIAS, grads[(LARGE_WARMUP + k) % 16], cut)
+            if k % 10 == 9:
+                sweeps.append(ell.ell.last_sweep_ms())   # event query of the most recent sweep (waits for it only)
+        a1.record(stream)
+        barrier()
+        t_large = max_over_ranks(a0.elapsed_time(a1) / 1e3)
+        l_launch = ell.ell.launches - l0
+        status = int(ell.ell.last_status())
+        sweep_ms = float(np.median(sweeps))
+        bytes_update = 16.0 * n * n                       # read M once + write M once
+        gbs = bytes_update * LARGE_UPDATES / t_large / 1e9
+        slab_bytes = bytes_update / world
+        large = {
+            "metric": "Ell::update HBM GB/s at n=16384 (whole job, 16*n^2 algorithmic bytes per update)",
+            "value": gbs, "unit": "GB/s", "updates_per_s": LARGE_UPDATES / t_large, "ms_per_update": 1e3 * t_large / LARGE_UPDATES,
+            "n": n, "updates": LARGE_UPDATES, "warmup": LARGE_WARMUP, "scaling": "strong", "reduce_mode": mode,
+            "last_status": status, "gpu_launches": int(l_launch),
+            "collective": None if world == 1 else "NCCL all_gather_into_tensor(grad_t, n*8 bytes) per update",
+            "roofline": {"bound": "hbm", "kernel": "sweep_kernel (fused deferred rank-1 + GEMV, TMA-staged)",
+                         "achieved": slab_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": slab_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": slab_bytes / (sweep_ms * 1e-3) / 1e9 / 8000.0,
+                         "ms_per_launch": sweep_ms, "algorithmic_bytes_per_launch": slab_bytes, "traffic": None},
+        }
+        # e2e: SearchSpace::update_bias_cut with a HOST gradient per call (H2D 8n bytes, D2H status) — whole matrix only
+        if world == 1:
+            hg = [torch.from_numpy(W.large_n_grad(n, k)).pin_memory() for k in range(8)]
+            st = C.c_int32()
+            K2 = 50
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for k in range(K2):
+                check(L.ellcuda_update(ell.ell._h, A.UPDATE_BIAS, hg[k % 8].data_ptr(), cut.beta0, 1, cut.beta1, C.byref(st)))
+            t1 = time.perf_counter() - t0
+            large["e2e"] = {"value": bytes_update * K2 / t1 / 1e9, "unit": "GB/s", "updates_per_s": K2 / t1,
+                            "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4, "updates": K2,
+                            "timing": "host wall clock around synchronous ellcuda_update calls"}
+        del ell
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ellref_py as R
+        T = R.hardware_threads()
+        sample = max(4 * T, 32)
+        sp = W.lowpass(sample, table, n=N_TAPS)
+        t0 = time.perf_counter()
+        o = R.solve(sp, T)
+        dt = time.perf_counter() - t0
+        it = iterations_done(o.num_iters, o.exit_status)
+        cpu = {"value": it / dt, "unit": "iterations/s", "cores": T, "kind": "port",
+               "sample": f"first {sample} problems of the same lowpass n=32 batch ({it} iterations, {dt:.1f} s), std::thread over problems",
+               "per_core": it / dt / T}
+        # parity spot check on the sample (the checker as checker)
+        g_it = dres["num_iters"][:sample].cpu().numpy()
+        cpu["sample_num_iters_identical"] = bool(np.array_equal(g_it, o.num_iters))
+        if large is not None:
+            nn = args.large_n
+            mq, xc = np.eye(nn), np.zeros(nn)
+            kap, tsq = C.c_double(1.0), C.c_double(0.0)
+            g = W.large_n_grad(nn, 0)
+            reps = 2
+            t0 = time.perf_counter()
+            for k in range(reps):
+                R.lib().ellref_ell_update_inplace(nn, mq.ctypes.data, xc.ctypes.data, C.byref(kap), C.byref(tsq), 0, 1, 0,
+                                                  g.ctypes.data, W.LARGE_N_CUT[0], 1, W.LARGE_N_CUT[1], None)
+            dt = (time.perf_counter() - t0) / reps
+            large["cpu_baseline"] = {"value": 16.0 * nn * nn / dt / 1e9, "unit": "GB/s", "s_per_update": dt, "cores": 1,
+                                     "kind": "port", "sample": f"{reps} updates of the reference algorithm (single-threaded, as the Rust code is)"}
+
+    if rank == 0:
+        alg_bytes = iters_step * 16.0 * N_TAPS * N_TAPS
+        line = {
+            "metric": "ellipsoid iterations/sec (batched n=32)", "value": value, "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "iterations_per_step_per_gpu": iters_step,
+            "roofline": {"bound": "hbm", "kernel": "batch_warp_kernel<OrLowpass> (persistent, one warp per problem)",
+                         "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                         "ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes, "traffic": None,
+                         "note": "equivalent-streaming figure of SURVEY.md 8d: 16*n^2 bytes per iteration (M read once, written "
+                                 "once) although M never leaves the register file; see large_n.roofline for the kernel that "
+                                 "really streams HBM"},
+            "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+            "large_n": large,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

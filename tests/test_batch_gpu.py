@@ -112,7 +112,7 @@ def test_bowl_reference_case(ref):  # tests/integration_test.rs:107-131: n=5, ta
 
 def test_bowl_flags(ref):
     for kw in (dict(no_defer_trick=True), dict(max_iters=2000), dict(max_iters=1)):
-        prob = W.bowl(16, n=32, **({"max_iters": 500} | kw))
+        prob = W.bowl(16, n=32, max_iters=kw.get("max_iters", 500))
         prob.no_defer_trick = kw.get("no_defer_trick", False)
         g, r = both(ref, prob)
         assert_parity(g, r, exact=True, what=str(kw))
