@@ -64,7 +64,9 @@ class ShardedEll:
         self.lo, self.hi = shard_range(n, self.rank, self.world)
         self.ell = Ell(kappa, xc, mq=mq, diag=diag, device=self.device, no_defer_trick=no_defer_trick,
                        use_parallel_cut=use_parallel_cut, rows=(self.lo, self.hi), reduce_mode=reduce_mode)
-        self.ell.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # run on torch's current stream so that the NCCL exchange is ordered with the sweeps; torch reports the legacy
+        # default stream as handle 0, which the C ABI reads as "own stream" — cudaStreamLegacy (0x1) names it explicitly
+        self.ell.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
         self.grad_t = torch.as_tensor(self.ell.grad_t_view(), device=f"cuda:{self.device}")
         self.even = n % self.world == 0
 

@@ -131,7 +131,8 @@ typedef struct ell_batch_desc {
     int32_t device;           /* CUDA device ordinal                                      */
     int32_t on_device;        /* 0: every pointer is host memory (copied in/out inside the
                                     call); 1: every pointer is device memory on `device`   */
-    void*   stream;           /* cudaStream_t to run on, NULL ⇒ the library's own stream   */
+    void*   stream;           /* cudaStream_t to run on; NULL ⇒ the library's own stream (to name
+                                 the legacy default stream pass cudaStreamLegacy, (void*)1)      */
 } ell_batch_desc;
 
 typedef struct ell_batch_result { /* caller-allocated; optional members may be NULL       */
@@ -183,7 +184,7 @@ typedef struct ell_create_desc {
                                   k>0: each row sum split into k ordered segments and omega
                                   reduced blockwise — deterministic, ≤1e-13 rel. of mode 0 */
     int32_t _pad0;
-    void*   stream;            /* cudaStream_t, NULL ⇒ own stream                          */
+    void*   stream;            /* cudaStream_t; NULL ⇒ own stream, (void*)1 = cudaStreamLegacy */
 } ell_create_desc;
 
 int  ellcuda_create(const ell_create_desc* desc, ell_handle* out); /* Ell::new* src/ell.rs:31-78 */
