@@ -19,7 +19,7 @@ EXPORTS = [
     "ellcuda_kappa", "ellcuda_get_mq", "ellcuda_update", "ellcuda_update_begin", "ellcuda_update_finish",
     "ellcuda_grad_t_ptr", "ellcuda_status_ptr", "ellcuda_last_status", "ellcuda_set_stream", "ellcuda_sync",
     "ellcuda_set_timing", "ellcuda_last_sweep_ms", "ellcuda_handle_launch_count",
-    "ellcuda_last_error", "ellcuda_version", "ellcuda_device_count",
+    "ellcuda_math_probe", "ellcuda_last_error", "ellcuda_version", "ellcuda_device_count",
 ]
 
 
@@ -60,6 +60,8 @@ def lib():
     L.ellcuda_lowpass_band_edge.argtypes = [C.c_int32, C.c_double]
     L.ellcuda_lowpass_band_edge.restype = C.c_int32
     L.ellcuda_last_error.restype = C.c_char_p
+    L.ellcuda_math_probe.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+    L.ellcuda_math_probe.restype = C.c_int
     L.ellcuda_version.restype = C.c_int
     L.ellcuda_device_count.restype = C.c_int
     if hasattr(L, "ellcuda_create"):

@@ -8,8 +8,10 @@
 //   EllStable::update_core                            src/ell_stable.rs:52-125
 // with the oracles of src/example1.rs, example1_rr.rs, example3.rs, example4.rs, quasicvx.rs,
 // src/oracles/profit_oracle.rs and the fixtures of tests/cutting_plane_tests.rs, tests/example2_tests.rs.
-// Compiled with -fmad=false: no contraction, sums in the reference's order.
+// Compiled with -fmad=false: no contraction, sums in the reference's order.  exp/ln are glibc's, bit for bit
+// (glibc_math.cuh), because that is what f64::exp / f64::ln are on the reference's platform.
 #include "common.cuh"
+#include "glibc_math.cuh"
 
 namespace ellcuda {
 namespace {
@@ -238,15 +240,15 @@ struct OrQuasicvx {  // src/quasicvx.rs:11-51
         for (int k = 0; k < 2; ++k) {
             idx += 1;
             if (idx == 2) idx = 0;
-            const double fv = idx == 0 ? sqrtx * sqrtx - logy : -sqrtx + gamma * exp(logy);
+            const double fv = idx == 0 ? sqrtx * sqrtx - logy : -sqrtx + gamma * glibc::exp(logy);
             if (fv > 0.0) {
                 if (idx == 0) { g[0] = 2.0 * sqrtx; g[1] = -1.0; }
-                else { g[0] = -1.0; g[1] = gamma * exp(logy); }
+                else { g[0] = -1.0; g[1] = gamma * glibc::exp(logy); }
                 cut = single_cut(fv);
                 return false;
             }
         }
-        gamma = sqrtx / exp(logy);
+        gamma = sqrtx / glibc::exp(logy);
         g[0] = -1.0; g[1] = sqrtx; cut = single_cut(0.0);
         return true;
     }
@@ -257,8 +259,8 @@ struct OrProfit {  // src/oracles/profit_oracle.rs:42-114
     double log_p_scale, log_k, v0, v1, a0, a1, log_cobb, vx, q0, q1;
     __device__ void setup(double p, double scale, double limit, double a0_, double a1_, double v0_, double v1_) {  // :54-68
         idx = -1;
-        log_p_scale = log(p * scale);
-        log_k = log(limit);
+        log_p_scale = glibc::log(p * scale);
+        log_k = glibc::log(limit);
         a0 = a0_; a1 = a1_; v0 = v0_; v1 = v1_;
         log_cobb = 0.0; vx = 0.0; q0 = 0.0; q1 = 0.0;
     }
@@ -278,10 +280,10 @@ struct OrProfit {  // src/oracles/profit_oracle.rs:42-114
                 dotv += a0 * y[0];
                 dotv += a1 * y[1];
                 log_cobb = log_p_scale + dotv;
-                q0 = v0 * exp(y[0]);
-                q1 = v1 * exp(y[1]);
+                q0 = v0 * glibc::exp(y[0]);
+                q1 = v1 * glibc::exp(y[1]);
                 vx = q0 + q1;
-                fj = log(gamma + vx) - log_cobb;
+                fj = glibc::log(gamma + vx) - log_cobb;
             }
             if (fj > 0.0) {
                 if (idx == 0) { g[0] = 1.0; g[1] = 0.0; }
@@ -299,7 +301,7 @@ struct OrProfit {  // src/oracles/profit_oracle.rs:42-114
     __device__ bool assess_optim(const double (&y)[2], double& gamma, double (&g)[2], Cut& cut) {  // :104-113
         double fj;
         if (feas(y, gamma, g, fj)) { cut = single_cut(fj); return false; }
-        const double exp_val = exp(log_cobb);
+        const double exp_val = glibc::exp(log_cobb);
         gamma = exp_val - vx;
         const double inv = 1.0 / exp_val;
         g[0] = q0 * inv - a0;
@@ -342,10 +344,10 @@ struct OrProfitQ {  // src/oracles/profit_oracle.rs:163-198
                 more_alt = true;
                 return false;
             }
-            double d0 = round(exp(y[0])), d1 = round(exp(y[1]));  // f64::round: half away from zero == CUDA round()
+            double d0 = round(glibc::exp(y[0])), d1 = round(glibc::exp(y[1]));  // f64::round: half away from zero == CUDA round()
             if (d0 == 0.0) d0 = 1.0;
             if (d1 == 0.0) d1 = 1.0;
-            yd[0] = log(d0); yd[1] = log(d1);
+            yd[0] = glibc::log(d0); yd[1] = glibc::log(d1);
         }
         const bool shrunk = omega.assess_optim(yd, gamma, g, cut);
         double dotv = 0.0;  // grad.dot(&(&yd - y))
@@ -560,6 +562,17 @@ int launch_kind(const BatchArgs& a, cudaStream_t s, int sm_count) {
 }
 
 }  // namespace
+
+__global__ void math_probe_kernel(int which, const double* __restrict__ x, double* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = which == 0 ? glibc::exp(x[i]) : glibc::log(x[i]);
+}
+
+int launch_math_probe(int which, const double* x, double* y, long long n, cudaStream_t s) {
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(which, x, y, n);
+    ELL_CUDA_TRY(cudaGetLastError());
+    return ELLCUDA_OK;
+}
 
 int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     if (a.n != 2) { set_error("this oracle is defined for n = 2"); return ELLCUDA_E_ARG; }

@@ -241,6 +241,27 @@ int32_t ellcuda_lowpass_band_edge(int32_t n, double w) {
     return (int32_t)std::floor(w * (double)(mdim - 1)) + 1;
 }
 
+// Diagnostic: y[i] = exp(x[i]) (which = 0) or ln(x[i]) (which = 1) with the DEVICE routines the oracles use
+// (glibc_math.cuh), host buffers in and out.  Lets a test prove they equal the host libm bit for bit.
+int ellcuda_math_probe(int32_t which, const double* x_host, double* y_host, int64_t n, int32_t device) {
+    using namespace ellcuda;
+    if (!x_host || !y_host || n < 0 || which < 0 || which > 1) { set_error("bad arguments"); return ELLCUDA_E_ARG; }
+    DeviceInfo* di = nullptr;
+    int rc = device_info(device, &di);
+    if (rc) return rc;
+    ELL_CUDA_TRY(cudaSetDevice(device));
+    if (n == 0) return ELLCUDA_OK;
+    cudaStream_t s = di->stream;
+    Scratch scratch(s);
+    void *dx = nullptr, *dy = nullptr;
+    if ((rc = scratch.alloc(&dx, (size_t)n * 8)) || (rc = scratch.alloc(&dy, (size_t)n * 8))) return rc;
+    ELL_CUDA_TRY(cudaMemcpyAsync(dx, x_host, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_math_probe(which, (const double*)dx, (double*)dy, n, s))) return rc;
+    ELL_CUDA_TRY(cudaMemcpyAsync(y_host, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    ELL_CUDA_TRY(cudaStreamSynchronize(s));
+    return ELLCUDA_OK;
+}
+
 const char* ellcuda_last_error(void) { return ellcuda::g_err.c_str(); }
 int ellcuda_version(void) { return 100; }
 int ellcuda_device_count(void) {

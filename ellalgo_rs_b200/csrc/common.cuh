@@ -53,6 +53,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // launchers implemented per kernel family; each returns ELLCUDA_* and adds to *launches
 int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
+int launch_math_probe(int which, const double* x_dev, double* y_dev, long long n, cudaStream_t s);
 int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 
 }  // namespace ellcuda

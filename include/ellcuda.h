@@ -227,6 +227,11 @@ int ellcuda_set_timing(ell_handle h, int32_t on);
 float ellcuda_last_sweep_ms(ell_handle h);
 int64_t ellcuda_handle_launch_count(ell_handle h);
 
+/* Diagnostic: y[i] = exp(x[i]) (which=0) / ln(x[i]) (which=1) computed with the device routines the built-in
+ * oracles use; they reproduce glibc's f64 exp/ln (what Rust's f64::exp / f64::ln call, profit_oracle.rs:54-113)
+ * bit for bit, and this entry point lets a test check that against the host libm.  Host buffers.            */
+int ellcuda_math_probe(int32_t which, const double* x_host, double* y_host, int64_t n, int32_t device);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* ellcuda_last_error(void);   /* thread-local, never NULL                          */
 int ellcuda_version(void);              /* 100*major + minor                                 */

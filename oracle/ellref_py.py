@@ -75,6 +75,7 @@ def lib():
         L.ellref_bsearch_bs2.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_int)]
         L.ellref_bsearch_bs2.restype = C.c_int64
         L.ellref_hardware_threads.restype = C.c_int
+        L.ellref_libm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         _lib = L
     return _lib
 
@@ -140,6 +141,14 @@ def calc(n, fn, b0=0.0, b1=None, tsq=0.0, a3=0.0, a4=0.0, use_parallel_cut=True)
     st = lib().ellref_calc(n, int(use_parallel_cut), fn, b0, 1 if b1 is not None else 0, 0.0 if b1 is None else b1, tsq, a3, a4,
                            out.ctypes.data)
     return st, tuple(out)
+
+
+def libm(which: int, x: np.ndarray) -> np.ndarray:
+    """glibc exp (0) / log (1) elementwise — numpy's own SIMD exp/log are NOT libm's"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    lib().ellref_libm(which, x.ctypes.data, y.ctypes.data, x.size)
+    return y
 
 
 def lowpass_table(n: int) -> np.ndarray:

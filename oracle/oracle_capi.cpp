@@ -288,6 +288,11 @@ int ellref_profit_assess(const double* p7, const double* y, double* gamma, doubl
     return a.second ? 1 : 0;
 }
 
+// the host libm the restatement itself uses (what Rust's f64::exp / f64::ln call): which = 0 exp, 1 ln
+void ellref_libm(int which, const double* x, double* y, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) y[i] = which == 0 ? std::exp(x[i]) : std::log(x[i]);
+}
+
 void ellref_lowpass_table(int64_t n, double* out) {
     const Vec s = lowpass_spectrum(static_cast<std::size_t>(n));
     std::copy(s.begin(), s.end(), out);

@@ -18,6 +18,31 @@ def both(ref, prob):
     return batch.solve_batch(prob), ref.solve(prob)
 
 
+# ------------------------------------------------------------------ device exp/ln == host libm
+def test_device_exp_ln_equal_glibc(ref):
+    """The oracles' exp/ln on the device (csrc/glibc_math.cuh) must equal the host's libm — what Rust's f64::exp /
+    f64::ln call (src/oracles/profit_oracle.rs:54-113) — in every bit, special values included."""
+    import ctypes as C
+    from ellalgo_rs_b200._lib import check, lib
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    x = np.concatenate([rng.uniform(-10, 10, n), rng.uniform(-745, 710, n), rng.uniform(-1e-3, 1e-3, n),
+                        rng.integers(0, 2**64, n, dtype=np.uint64).view(np.float64),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 709.782712893384, -745.1332191019412, 1e-320]])
+    y = np.empty_like(x)
+    check(lib().ellcuda_math_probe(0, x.ctypes.data, y.ctypes.data, x.size, 0))
+    want = ref.libm(0, x)      # numpy's SIMD exp is not libm's; the checker calls glibc
+    same = (y.view(np.uint64) == want.view(np.uint64)) | (np.isnan(y) & np.isnan(want))
+    assert same.all(), f"exp differs at {x[~same][:5]}"
+    x = np.concatenate([rng.uniform(0.9, 1.1, n), np.exp(rng.uniform(-5, 15, n)), rng.uniform(0, 1e-310, n),
+                        rng.integers(0, 2**64, n, dtype=np.uint64).view(np.float64),
+                        [0.0, -0.0, 1.0, np.inf, -1.0, np.nan, 5e-324, 1.7976931348623157e308]])
+    check(lib().ellcuda_math_probe(1, x.ctypes.data, y.ctypes.data, x.size, 0))
+    want = ref.libm(1, x)
+    same = (y.view(np.uint64) == want.view(np.uint64)) | (np.isnan(y) & np.isnan(want))
+    assert same.all(), f"ln differs at {x[~same][:5]}"
+
+
 # ------------------------------------------------------------------ n = 2, thread per problem
 def test_example1_pinned(ref):  # src/example1.rs:39-50
     g, r = both(ref, W.example1())
@@ -57,20 +82,20 @@ def test_fixtures_n2(ref, name, kw, pinned, kind):
 
 
 @pytest.mark.parametrize("kind", [A.KIND_ELL, A.KIND_ELLSTABLE])
-def test_quasicvx(ref, kind):  # src/quasicvx.rs:61-131 (exp on device vs glibc: tolerance, not bits)
+def test_quasicvx(ref, kind):  # src/quasicvx.rs:61-131 (device exp == glibc exp, so bit-identical)
     prob = BatchProblem(oracle_id=A.ORACLE_QUASICVX, n=2, count=1, kind=kind, kappa0=1.0, diag0=[10.0, 10.0], gamma0=0.0,
                         tolerance=1e-8)
     g, r = both(ref, prob)
     if kind == A.KIND_ELL:
         assert g.num_iters[0] == 35
-    assert_parity(g, r, exact=False, what="quasicvx")
+    assert_parity(g, r, exact=True, what="quasicvx")
 
 
 def test_profit_pinned_and_random(ref):  # src/oracles/profit_oracle.rs:207-223 + C2 generator
-    prob = W.profit(20000)
+    prob = W.profit(200000)
     g, r = both(ref, prob)
     assert g.num_iters[0] == 83 and g.xbest[0, 0] <= math.log(30.5)
-    assert_parity(g, r, exact=False, what="profit")
+    assert_parity(g, r, exact=True, what="profit")
 
 
 def test_profit_rb_and_q(ref):  # :225-260
@@ -79,12 +104,12 @@ def test_profit_rb_and_q(ref):  # :225-260
     p.params = np.concatenate([W.PROFIT_REF, [0.003, 0.007, 1.0, 1.0, 1.0]])
     g, r = both(ref, p)
     assert g.num_iters[0] == 90
-    assert_parity(g, r, exact=False, what="profit_rb")
+    assert_parity(g, r, exact=True, what="profit_rb")
     p = W.profit(4096)
     p.oracle_id, p.mode = A.ORACLE_PROFIT_Q, A.MODE_OPTIM_Q
     g, r = both(ref, p)
     assert g.num_iters[0] == 29
-    assert_parity(g, r, exact=False, what="profit_q")
+    assert_parity(g, r, exact=True, what="profit_q")
 
 
 def test_flags_n2(ref):

@@ -1,0 +1,23 @@
+"""short, deterministic workload for ncu: one lowpass n=32 batch launch + a few large-n updates"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from ellalgo_rs_b200 import batch, workloads as W, _abi as A
+from ellalgo_rs_b200.ell import Ell
+from ellalgo_rs_b200.cutting_plane import ParallelCut
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+if what in ("all", "batch"):
+    t = batch.lowpass_table(32)
+    o = batch.solve_batch(W.lowpass(int(os.environ.get("PROF_COUNT", "4736")), t))   # 2 problems per resident warp
+    print("lowpass iterations", int(o.num_iters.sum()))
+    o = batch.solve_batch(W.bowl(int(os.environ.get("PROF_COUNT", "4736")) * 2, n=32, max_iters=2000))
+    print("bowl iterations", int(o.num_iters.sum()))
+if what in ("all", "stream"):
+    n = 16384
+    e = Ell.new_with_scalar(1.0, np.zeros(n))
+    gs = [torch.from_numpy(W.large_n_grad(n, k)).cuda() for k in range(4)]
+    for k in range(5):
+        e.update_begin(A.UPDATE_BIAS, gs[k % 4].data_ptr(), ParallelCut(*W.LARGE_N_CUT)); e.update_finish()
+    e.sync()
+    print("large-n status", e.last_status(), e.kappa)
