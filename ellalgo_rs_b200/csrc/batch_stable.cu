@@ -1,8 +1,376 @@
-// batch_stable.cu — placeholder, replaced by the EllStable + LMI kernel.
+// batch_stable.cu — batched cutting_plane_feas with EllStable and the LMI oracle: ONE WARP PER PROBLEM, persistent.
+//
+//   cutting_plane_feas                 src/cutting_plane.rs:205-227
+//   EllStable::update_core             src/ell_stable.rs:52-125      (LDLᵀ-form update)
+//   LMIOracle::assess_feas             src/oracles/lmi_oracle.rs:24-44
+//   LDLTMgr::factor/witness/sym_quad   src/oracles/ldlt_mgr.rs:29-55, 98-111, 115-124
+//
+// n <= 64 variables (lane L owns indices L and L+32), LMI size m <= 32.  The F_k matrices (shared by the batch) are
+// staged once per CTA in shared memory as packed lower triangles with an odd stride.  Every sum keeps the
+// reference's order: the forward substitution is done column by column (for each j, every i>j subtracts term j —
+// per element that is j ascending, as in the reference), the back substitution's per-row chain is sequential, the
+// LDLᵀ inner sums accumulate k ascending per column.  Two variants of the space:
+//   GENERAL  the full recurrence; strict upper triangle (the L factor) packed in shared memory (new_with_matrix)
+//   DIAG     EllStable::new / new_with_scalar start from a diagonal matrix, and under the reference's recurrence the
+//            strict upper triangle then stays exactly +0 forever: every O(n²) term is a multiply by
+//            zero, so the same results come from the O(n) diagonal recurrence.  Bit-identical for finite data (the
+//            LMI gradient sym_quad never yields -0.0; a non-finite gradient would differ in NaN placement only).
+// The strict lower triangle of the reference's matrix is scratch that no API can observe (EllStable's fields are
+// private, src/ell_stable.rs:9-15); it is recomputed on the fly instead of stored.
 #include "common.cuh"
+
 namespace ellcuda {
-int launch_batch_stable(const BatchArgs&, int, cudaStream_t, int, long long*) {
-    set_error("EllStable/LMI batched kernel not built yet");
-    return ELLCUDA_E_ARG;
+namespace {
+
+constexpr int kNMax = 64;
+
+__device__ __forceinline__ int tri_index(int i, int j) {  // packed lower triangle, j <= i
+    return i * (i + 1) / 2 + j;
 }
+__device__ __forceinline__ int upper_off(int r, int n) {  // packed upper triangle incl. diagonal: row r starts here
+    return r * n - r * (r - 1) / 2;
+}
+__device__ __forceinline__ double bcast(double lo, double hi, int idx) {
+    const double a = __shfl_sync(0xffffffffu, lo, idx & 31);
+    const double b = __shfl_sync(0xffffffffu, hi, idx & 31);
+    return idx < 32 ? a : b;
+}
+
+struct WarpMem {
+    double* sx;    // n   xc (oracle input)
+    double* sv;    // n   general scratch vector (products / gg)
+    double* sw;    // n   w = inv(L) g
+    double* sz;    // n   z
+    double* sa;    // tri(m)  LMI elements A(i,j), j <= i
+    double* st;    // m*m LDLT storage
+    double* swit;  // m   witness
+    double* qu;    // GENERAL only: packed upper triangle of the EllStable matrix
+};
+
+// ---------------------------------------------------------------------------------------------- LMI oracle
+struct LmiShared {
+    const double* fp;  // n × fstride packed lower triangles of F_k
+    const double* bp;  // tri packed lower triangle of B
+    int fstride, m, tri, nvar;
+};
+
+// returns true if a cut was produced: g0/g1 = this lane's gradient entries, ep = beta
+__device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, double& g0, double& g1, double& ep) {
+    const int m = L.m, tri = L.tri, n = L.nvar;
+    // --- elements A(i,j) = B[i][j] - sum_k F_k[i][j]*x[k], k ascending (src/oracles/lmi_oracle.rs:28-34)
+    for (int e0 = lane; e0 < tri; e0 += 32 * 4) {
+        double a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 32 * u;
+            a[u] = e < tri ? L.bp[e] : 0.0;
+        }
+        for (int k = 0; k < n; ++k) {
+            const double xk = wm.sx[k];
+            const double* fk = L.fp + k * L.fstride;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 32 * u;
+                if (e < tri) a[u] -= fk[e] * xk;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 32 * u;
+            if (e < tri) wm.sa[e] = a[u];
+        }
+    }
+    __syncwarp();
+    // --- LDLTMgr::factor (src/oracles/ldlt_mgr.rs:29-55); lane c follows column c of the current row
+    int pos = 0;
+    for (int i = 0; i < m; ++i) {
+        double acc = 0.0;                                   // s for column `lane`: sum_k T[i][k]*T[k][lane], k ascending
+        double diag = wm.sa[tri_index(i, 0)];               // get_elem(i, start)
+        for (int j = 0; j < i; ++j) {
+            const double d = __shfl_sync(0xffffffffu, diag, j);
+            const double val = d / wm.st[j * m + j];
+            if (lane == 0) {
+                wm.st[j * m + i] = d;                       // keep for later
+                wm.st[i * m + j] = val;                     // L[i][j]
+            }
+            const int c = lane;
+            if (c > j && c <= i) {
+                const double tjc = (c == i) ? d : wm.st[j * m + c];
+                acc += val * tjc;
+                if (c == j + 1) diag = wm.sa[tri_index(i, c)] - acc;   // get_elem(i, stop) - s
+            }
+        }
+        const double dii = __shfl_sync(0xffffffffu, diag, i);
+        if (lane == 0) wm.st[i * m + i] = dii;
+        __syncwarp();
+        if (dii <= 0.0) { pos = i + 1; break; }
+    }
+    if (pos == 0) return false;                             // is_spd
+    // --- witness (ldlt_mgr.rs:98-111), start = 0
+    const int mm = pos - 1;
+    if (lane == 0) wm.swit[mm] = 1.0;
+    __syncwarp();
+    for (int i = mm; i >= 1; --i) {
+        double s = 0.0;
+        for (int k = i; k < pos; ++k) s += wm.st[k * m + (i - 1)] * wm.swit[k];
+        __syncwarp();
+        if (lane == 0) wm.swit[i - 1] = -s;
+        __syncwarp();
+    }
+    ep = -wm.st[mm * m + mm];
+    // --- g[k] = sym_quad(F_k) (ldlt_mgr.rs:115-124): i outer, j inner, (wit[i]*F[i][j])*wit[j]
+    double r0 = 0.0, r1 = 0.0;
+    const int k0 = lane, k1 = lane + 32;
+    const double* f0 = L.fp + (k0 < n ? k0 : 0) * L.fstride;
+    const double* f1 = L.fp + (k1 < n ? k1 : 0) * L.fstride;
+    for (int i = 0; i < pos; ++i) {
+        const double wi = wm.swit[i];
+        for (int j = 0; j < pos; ++j) {
+            const double wj = wm.swit[j];
+            const int e = i >= j ? tri_index(i, j) : tri_index(j, i);
+            r0 += wi * f0[e] * wj;
+            r1 += wi * f1[e] * wj;
+        }
+    }
+    g0 = k0 < n ? r0 : 0.0;
+    g1 = k1 < n ? r1 : 0.0;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- EllStable update
+// sequential sum of n values held as (lo, hi) per lane, via shared memory; every lane gets the result
+__device__ __forceinline__ double seq_sum_pair(double* s, double lo, double hi, int lane, int n) {
+    s[lane] = lo;
+    if (lane + 32 < kNMax) s[lane + 32] = hi;
+    __syncwarp();
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += s[k];
+    __syncwarp();
+    return acc;
+}
+
+template <bool DIAG>
+__device__ int stable_update(const CalcConsts& cc, const WarpMem& wm, int lane, int n, double g0, double g1, const Cut& cut,
+                             double& d0, double& d1, double& xc0, double& xc1, double& kappa, double& tsq) {
+    const int i0 = lane, i1 = lane + 32;
+    const bool on0 = i0 < n, on1 = i1 < n;
+    // --- inv(L)*grad (src/ell_stable.rs:60-69)
+    double w0 = g0, w1 = g1;
+    if (!DIAG) {
+        for (int j = 0; j + 1 < n; ++j) {
+            const double wj = bcast(w0, w1, j);
+            const double* row = wm.qu + upper_off(j, n) - j;      // row[c] = Q[j][c], c >= j
+            if (on0 && i0 > j) w0 -= row[i0] * wj;
+            if (on1 && i1 > j) w1 -= row[i1] * wj;
+        }
+        d0 = on0 ? wm.qu[upper_off(i0, n)] : 0.0;
+        d1 = on1 ? wm.qu[upper_off(i1, n)] : 0.0;
+    }
+    // --- inv(D)*inv(L)*grad and omega (:72-83)
+    const double z0 = w0 * d0, z1 = w1 * d1;
+    const double gg0 = z0 * w0, gg1 = z1 * w1;
+    const double omega = seq_sum_pair(wm.sv, on0 ? gg0 : 0.0, on1 ? gg1 : 0.0, lane, n);   // sv now holds gg[]
+    tsq = kappa * omega;
+    Rsd r;
+    const int status = ell_calc(cc, kBias, cut, tsq, r);
+    if (status != kSuccess) return status;
+    // --- mq*grad = inv(L')*inv(D)*inv(L)*grad (:93-98): q[c] = z[c] - sum_{j>c, ascending} (Q[c][j]*w[c])*q[j]
+    double q0 = z0, q1 = z1;
+    if (!DIAG) {
+        wm.sw[lane] = w0;
+        if (i1 < kNMax) wm.sw[i1] = w1;
+        __syncwarp();
+        for (int c = n - 2; c >= 0; --c) {
+            const double wc = wm.sw[c];
+            const double* row = wm.qu + upper_off(c, n) - c;
+            if (on0 && i0 > c) wm.sz[i0] = (row[i0] * wc) * q0;   // the scratch entry val(j,c) = Q[c][j]*w[c], times q[j]
+            if (on1 && i1 > c) wm.sz[i1] = (row[i1] * wc) * q1;
+            __syncwarp();
+            double qc = bcast(q0, q1, c);
+            for (int j = c + 1; j < n; ++j) qc -= wm.sz[j];
+            if (i0 == c) q0 = qc;
+            if (i1 == c) q1 = qc;
+            __syncwarp();
+        }
+    }
+    // --- xc (:101-104)
+    const double rho_over_omega = r.rho / omega;
+    xc0 -= rho_over_omega * q0;
+    xc1 -= rho_over_omega * q1;
+    // --- rank-one update of the factor (:107-121)
+    const double mu = r.sigma / (1.0 - r.sigma);
+    double oldt = omega / mu;
+    double oldt0 = 0.0, t0 = 1.0, oldt1 = 0.0, t1 = 1.0;
+    for (int j = 0; j < n; ++j) {            // temp = oldt + gg[j]; oldt = temp   — one ordered chain, every lane
+        const double temp = oldt + wm.sv[j];
+        if (j == i0) { oldt0 = oldt; t0 = temp; }
+        if (j == i1) { oldt1 = oldt; t1 = temp; }
+        oldt = temp;
+    }
+    const double nd0 = d0 * (oldt0 / t0), nd1 = d1 * (oldt1 / t1);   // mq[j][j] *= oldt / temp
+    if (DIAG) {
+        d0 = nd0;
+        d1 = nd1;
+    } else {
+        const double b0 = z0 / t0, b1 = z1 / t1;                       // beta2 = inv_md_inv_ml_g[j] / temp
+        __syncwarp();
+        wm.sz[lane] = b0;
+        if (i1 < kNMax) wm.sz[i1] = b1;
+        __syncwarp();
+        for (int j = 0; j + 1 < n; ++j) {                              // mq[j][l] += beta2 * mq[l][j],  l > j
+            const double bj = wm.sz[j], wj = wm.sw[j];
+            double* row = wm.qu + upper_off(j, n) - j;
+            if (on0 && i0 > j) { const double v = row[i0]; row[i0] = v + bj * (v * wj); }
+            if (on1 && i1 > j) { const double v = row[i1]; row[i1] = v + bj * (v * wj); }
+        }
+        if (on0) wm.qu[upper_off(i0, n)] = nd0;
+        if (on1) wm.qu[upper_off(i1, n)] = nd1;
+        __syncwarp();
+    }
+    kappa *= r.delta;   // :122
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <bool DIAG>
+__global__ void __launch_bounds__(512) batch_stable_kernel(const BatchArgs a, int warps, int fstride, int per_warp_doubles) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = a.n, m = a.aux[0], tri = m * (m + 1) / 2;
+    // stage F_k (packed lower, odd stride) and B once per CTA
+    double* fp = smem;
+    double* bp = fp + (long long)n * fstride;
+    for (int idx = threadIdx.x; idx < n * tri; idx += blockDim.x) {
+        const int k = idx / tri, e = idx - k * tri;
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (tri_index(i + 1, 0) <= e) ++i;
+        while (tri_index(i, 0) > e) --i;
+        const int j = e - tri_index(i, 0);
+        fp[k * fstride + e] = a.table[(long long)k * m * m + i * m + j];
+    }
+    for (int e = threadIdx.x; e < tri; e += blockDim.x) {
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (tri_index(i + 1, 0) <= e) ++i;
+        while (tri_index(i, 0) > e) --i;
+        const int j = e - tri_index(i, 0);
+        bp[e] = a.table[(long long)n * m * m + i * m + j];
+    }
+    __syncthreads();
+    long long base = (long long)n * fstride + tri;
+    base = (base + 1) & ~1LL;
+    double* ws = smem + base + (long long)warp * per_warp_doubles;
+    WarpMem wm;
+    wm.sx = ws; wm.sv = ws + kNMax; wm.sw = ws + 2 * kNMax; wm.sz = ws + 3 * kNMax;
+    wm.sa = ws + 4 * kNMax;
+    wm.st = wm.sa + ((tri + 1) & ~1);
+    wm.swit = wm.st + m * m;
+    wm.qu = wm.swit + ((m + 1) & ~1);
+    LmiShared L{fp, bp, fstride, m, tri, n};
+    const CalcConsts cc = CalcConsts::make(n, a.use_parallel_cut);
+    const int i0 = lane, i1 = lane + 32;
+    const bool on0 = i0 < n, on1 = i1 < n;
+    (void)warps;
+
+    for (;;) {
+        unsigned long long pid_u = 0;
+        if (lane == 0) pid_u = atomicAdd(a.queue, 1ULL);
+        pid_u = __shfl_sync(0xffffffffu, pid_u, 0);
+        const long long pid = (long long)pid_u;
+        if (pid >= a.count) break;
+
+        double d0 = 0.0, d1 = 0.0;
+        if (DIAG) {   // EllStable::new / new_with_scalar (src/ell_stable.rs:29-35)
+            d0 = on0 ? (a.diag0 ? a.diag0[pid * a.diag0_stride + i0] : 1.0) : 0.0;
+            d1 = on1 ? (a.diag0 ? a.diag0[pid * a.diag0_stride + i1] : 1.0) : 0.0;
+        } else {      // new_with_matrix: diagonal + strict upper triangle are the state
+            const double* mq = a.mq0 + pid * a.mq0_stride;
+            for (int r = 0; r < n; ++r) {
+                double* row = wm.qu + upper_off(r, n) - r;
+                if (on0 && i0 >= r) row[i0] = mq[(long long)r * n + i0];
+                if (on1 && i1 >= r) row[i1] = mq[(long long)r * n + i1];
+            }
+            __syncwarp();
+        }
+        double xc0 = on0 ? a.xc0[pid * a.xc0_stride + i0] : 0.0;
+        double xc1 = on1 ? a.xc0[pid * a.xc0_stride + i1] : 0.0;
+        double kappa = a.kappa0[pid * a.kappa0_stride];
+        double tsq = 0.0;
+        bool has_best = false;
+        long long niter = 0;
+        int exit_status = kExitMaxIt;
+
+        for (; niter < a.max_iters; ++niter) {   // cutting_plane_feas, src/cutting_plane.rs:215-225
+            wm.sx[lane] = xc0;
+            if (i1 < kNMax) wm.sx[i1] = xc1;
+            __syncwarp();
+            double g0 = 0.0, g1 = 0.0, ep = 0.0;
+            if (!lmi_assess(L, wm, lane, g0, g1, ep)) {
+                has_best = true;
+                exit_status = kExitFeasible;
+                break;
+            }
+            const int status = stable_update<DIAG>(cc, wm, lane, n, g0, g1, single_cut(ep), d0, d1, xc0, xc1, kappa, tsq);
+            if (status != kSuccess) { exit_status = status; break; }
+            if (tsq < a.tolerance) { exit_status = kExitTol; break; }
+        }
+        if (lane == 0) {
+            a.num_iters[pid] = niter;
+            a.exit_status[pid] = exit_status;
+            if (a.has_xbest) a.has_xbest[pid] = has_best ? 1 : 0;
+            if (a.gamma) a.gamma[pid] = 0.0;
+            if (a.tsq) a.tsq[pid] = tsq;
+            if (a.kappa) a.kappa[pid] = kappa;
+        }
+        if (on0) {
+            if (a.xbest && has_best) a.xbest[pid * n + i0] = xc0;
+            if (a.xc) a.xc[pid * n + i0] = xc0;
+        }
+        if (on1) {
+            if (a.xbest && has_best) a.xbest[pid * n + i1] = xc1;
+            if (a.xc) a.xc[pid * n + i1] = xc1;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
+    if (oracle_id != ELL_ORACLE_LMI) { set_error("this oracle has no device implementation yet"); return ELLCUDA_E_ARG; }
+    if (a.kind != ELL_KIND_ELLSTABLE || a.mode != ELL_MODE_FEAS) {
+        set_error("the LMI device oracle runs under cutting_plane_feas with EllStable");
+        return ELLCUDA_E_ARG;
+    }
+    const int n = a.n, m = a.aux[0];
+    if (n < 1 || n > kNMax) { set_error("LMI kernel needs 1 <= n <= 64"); return ELLCUDA_E_ARG; }
+    if (m < 1 || m > 32) { set_error("LMI kernel needs 1 <= m <= 32"); return ELLCUDA_E_ARG; }
+    if (!a.table || a.table_len < (long long)(n + 1) * m * m) { set_error("LMI needs table = F_0..F_{n-1}, B"); return ELLCUDA_E_ARG; }
+    const int tri = m * (m + 1) / 2;
+    const int fstride = tri | 1;
+    const bool diag = a.mq0 == nullptr;
+    int per_warp = 4 * kNMax + ((tri + 1) & ~1) + m * m + ((m + 1) & ~1);
+    if (!diag) per_warp += (n * (n + 1) / 2 + 1) & ~1;
+    per_warp = (per_warp + 1) & ~1;
+    const size_t fixed = (((size_t)n * fstride + tri + 1) & ~(size_t)1) * 8;
+    const size_t budget = 227 * 1024;
+    if (fixed + (size_t)per_warp * 8 > budget) { set_error("F table too large for shared memory"); return ELLCUDA_E_ARG; }
+    int warps = (int)((budget - fixed) / ((size_t)per_warp * 8));
+    if (warps > 16) warps = 16;
+    const size_t smem = fixed + (size_t)warps * per_warp * 8;
+    long long blocks = sm_count;
+    const long long need = (a.count + warps - 1) / warps;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    if (diag) {
+        ELL_CUDA_TRY(cudaFuncSetAttribute(batch_stable_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        batch_stable_kernel<true><<<(unsigned)blocks, warps * 32, smem, s>>>(a, warps, fstride, per_warp);
+    } else {
+        ELL_CUDA_TRY(cudaFuncSetAttribute(batch_stable_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        batch_stable_kernel<false><<<(unsigned)blocks, warps * 32, smem, s>>>(a, warps, fstride, per_warp);
+    }
+    ELL_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 1;
+    return ELLCUDA_OK;
+}
+
 }  // namespace ellcuda

@@ -125,6 +125,20 @@ static int batch_solve_impl(const ell_batch_desc* d, const ell_batch_result* r) 
         return ELLCUDA_E_ARG;
     }
 
+    if (d->oracle_id == ELL_ORACLE_LMI && !d->on_device && d->table) {
+        // the device keeps F_k as packed lower triangles; sym_quad (ldlt_mgr.rs:115-124) reads both triangles, so the
+        // F_k must be symmetric — which an LMI requires anyway
+        const long long m = d->aux[0];
+        if (m >= 1 && d->table_len >= (long long)d->n * m * m)
+            for (long long k = 0; k < d->n; ++k)
+                for (long long i = 0; i < m; ++i)
+                    for (long long j = 0; j < i; ++j)
+                        if (!(d->table[k * m * m + i * m + j] == d->table[k * m * m + j * m + i])) {
+                            set_error("LMI: every F_k must be symmetric");
+                            return ELLCUDA_E_ARG;
+                        }
+    }
+
     Scratch scratch(s);
     BatchArgs a;
     memset(&a, 0, sizeof a);

@@ -99,15 +99,18 @@ def lmi_table(n: int = 64, m: int = 16) -> np.ndarray:
     return np.concatenate([f.reshape(-1), b.reshape(-1)])
 
 
-def lmi(count: int, n: int = 64, m: int = 16, first: int = 0, general: bool = False, table=None) -> BatchProblem:
+def lmi(count: int, n: int = 64, m: int = 16, first: int = 0, general: bool = False, table=None,
+        upper_scale: float = 0.1) -> BatchProblem:
     """C4: LMIOracle feasibility with EllStable.  C4a (general=False): EllStable::new_with_scalar(100, xc0);
-    C4b (general=True): new_with_matrix(100, U0, xc0), U0 = unit diagonal + strict upper U[-0.1,0.1]."""
+    C4b (general=True): new_with_matrix(100, U0, xc0), U0 = unit diagonal + strict upper U[-s,s], s = upper_scale.
+    (Under the reference's recurrence a non-zero upper triangle soon drives omega negative — runs end in NoSoln after
+    3-40 iterations depending on s; that is the reference's behaviour and is what parity is held to.)"""
     if table is None:
         table = lmi_table(n, m)
     xc0 = _uniform(SEED + 6, count, n, -1.0, 1.0, first)
     mq0 = None
     if general:
-        u = _uniform(SEED + 7, 1, n * n, -0.1, 0.1).reshape(n, n)
+        u = _uniform(SEED + 7, 1, n * n, -upper_scale, upper_scale).reshape(n, n)
         mq0 = np.triu(u, 1) + np.eye(n)
     return BatchProblem(oracle_id=_abi.ORACLE_LMI, n=n, count=count, mode=_abi.MODE_FEAS, kind=_abi.KIND_ELLSTABLE,
                         kappa0=100.0, xc0=xc0, mq0=mq0, table=table, aux=[m], max_iters=2000, tolerance=1e-20)

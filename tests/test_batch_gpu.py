@@ -196,3 +196,53 @@ def test_empty_batch_and_bad_args(ref):
     bad.mq0 = np.arange(16.0).reshape(4, 4)
     with pytest.raises(EllCudaError):
         batch.solve_batch(bad)
+
+
+# ------------------------------------------------------------------ EllStable + LMI (n <= 64), warp per problem
+def test_lmi_reference_matrices(ref):  # tests/lmi_tests.rs:14-64: (F1,B1) is feasible at 0; also a far-away start
+    f1 = np.array([-7, -11, -11, 3, 7, -18, -18, 8, -2, -8, -8, 1], dtype=float)
+    b1 = np.array([33, -9, -9, 26], dtype=float)
+    tab = np.concatenate([f1, b1])
+    for xc0 in ([0.0, 0.0, 0.0], [30.0, -20.0, 10.0], [1.0, 1.0, 1.0]):
+        prob = BatchProblem(oracle_id=A.ORACLE_LMI, n=3, count=2, mode=A.MODE_FEAS, kind=A.KIND_ELLSTABLE, kappa0=10.0,
+                            xc0=xc0, table=tab, aux=[2])
+        g, r = both(ref, prob)
+        assert_parity(g, r, exact=True, what=f"lmi 2x2 from {xc0}")
+    g, _ = both(ref, BatchProblem(oracle_id=A.ORACLE_LMI, n=3, count=1, mode=A.MODE_FEAS, kind=A.KIND_ELLSTABLE,
+                                  kappa0=10.0, table=tab, aux=[2]))
+    assert (g.has_xbest[0], g.num_iters[0], g.exit_status[0]) == (1, 0, A.EXIT_FEASIBLE)
+
+
+@pytest.mark.parametrize("n,m,count", [(64, 16, 96), (20, 7, 40), (33, 16, 17), (64, 5, 33)])
+def test_lmi_diagonal_start(ref, n, m, count):  # C4a: EllStable::new_with_scalar — the matrix stays diagonal
+    prob = W.lmi(count, n=n, m=m)
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"lmi diag n={n} m={m}")
+    assert (g.exit_status == A.EXIT_FEASIBLE).any()
+
+
+def test_lmi_diag_vector_start(ref):  # EllStable::new(val, xc)
+    prob = W.lmi(24, n=40, m=9)
+    prob.kappa0 = np.array([1.0])
+    prob.diag0 = np.random.default_rng(3).uniform(50, 150, size=(24, 40))
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what="lmi diag vector start")
+
+
+@pytest.mark.parametrize("n,m,count,scale", [(64, 16, 24, 0.1), (64, 16, 40, 1e-3), (64, 16, 40, 1e-6), (17, 6, 20, 0.05),
+                                             (40, 16, 9, 1e-4)])
+def test_lmi_general_start(ref, n, m, count, scale):  # C4b: new_with_matrix with a non-zero strict upper triangle
+    prob = W.lmi(count, n=n, m=m, general=True, upper_scale=scale)
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"lmi general n={n} m={m}")
+
+
+def test_lmi_bad_arguments():
+    from ellalgo_rs_b200._lib import EllCudaError
+    prob = W.lmi(2, n=8, m=4)
+    prob.table = prob.table.copy()
+    prob.table[1] += 1.0            # F_0 no longer symmetric
+    with pytest.raises(EllCudaError):
+        batch.solve_batch(prob)
+    with pytest.raises(EllCudaError):
+        batch.solve_batch(W.lmi(2, n=65, m=4))

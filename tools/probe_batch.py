@@ -16,3 +16,5 @@ run("bowl32 full", W.bowl(1 << 14, n=32, max_iters=20000))
 t = batch.lowpass_table(32)
 run("lowpass32", W.lowpass(4096, t))
 run("profit", W.profit(1 << 20))
+run("lmi64 diag", W.lmi(1 << 15, n=64, m=16))
+run("lmi64 general 1e-6", W.lmi(1 << 12, n=64, m=16, general=True, upper_scale=1e-6))
