@@ -1,0 +1,24 @@
+"""Generates tests/golden/golden_v1.npz with the CPU checker (oracle/).  The Rust reference cannot run in this image,
+so these vectors are NOT reference output: they freeze the checker's results (which reproduce every count the
+reference's tests pin) so that a later change to oracle/ or to the kernels is caught against a committed artefact.
+Run from the repo root:  python tests/golden/make_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import ellref_py as R  # noqa: E402
+from golden_cases import CASES, run_stepwise  # noqa: E402
+
+out = {}
+for name, make in CASES.items():
+    o = R.solve(make(R))
+    for f in ("xbest", "has_xbest", "num_iters", "exit_status", "gamma", "tsq", "xc", "kappa"):
+        out[f"{name}/{f}"] = getattr(o, f)
+st = run_stepwise(lambda **kw: R.Space(0, **kw), lambda s, w, g, b0, b1: s.update(w, g, b0, b1, single=False), lambda s: s.state())
+for k, v in st.items():
+    out[f"stepwise/{k}"] = v
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"), **out)
+print("wrote", len(out), "arrays")
