@@ -52,7 +52,7 @@ int device_info(int dev, DeviceInfo** out) {
         cudaDeviceProp p;
         ELL_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
         if (p.major < 10) { set_error("libellcuda is built for sm_100a (B200) only"); return ELLCUDA_E_CUDA; }
-        ELL_CUDA_TRY(cudaSetDevice(dev));
+        ELL_DEVICE_SCOPE(dev);
         ELL_CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
         d.sm_count = p.multiProcessorCount;
         d.major = p.major;
@@ -117,7 +117,7 @@ static int batch_solve_impl(const ell_batch_desc* d, const ell_batch_result* r) 
     DeviceInfo* di = nullptr;
     rc = device_info(d->device, &di);
     if (rc) return rc;
-    ELL_CUDA_TRY(cudaSetDevice(d->device));
+    ELL_DEVICE_SCOPE(d->device);
     cudaStream_t s = d->stream ? (cudaStream_t)d->stream : di->stream;
     if (d->count == 0) return ELLCUDA_OK;
     if (d->kind == ELL_KIND_ELL && d->mq0 && !d->on_device && !host_mq_symmetric(d)) {
@@ -263,7 +263,7 @@ int ellcuda_math_probe(int32_t which, const double* x_host, double* y_host, int6
     DeviceInfo* di = nullptr;
     int rc = device_info(device, &di);
     if (rc) return rc;
-    ELL_CUDA_TRY(cudaSetDevice(device));
+    ELL_DEVICE_SCOPE(device);
     if (n == 0) return ELLCUDA_OK;
     cudaStream_t s = di->stream;
     Scratch scratch(s);

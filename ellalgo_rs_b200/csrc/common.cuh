@@ -50,6 +50,23 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (_e != cudaSuccess) return ::ellcuda::cuda_fail(_e, #expr, __FILE__, __LINE__); \
     } while (0)
 
+// makes `dev` current for the scope of a C-ABI call and restores the caller's device afterwards (the library must
+// not change the process' current device behind torch's back)
+struct DevGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        err = cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ELL_DEVICE_SCOPE(dev)           \
+    ::ellcuda::DevGuard _dev_guard(dev); \
+    ELL_CUDA_TRY(_dev_guard.err)
+
 // launchers implemented per kernel family; each returns ELLCUDA_* and adds to *launches
 int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);

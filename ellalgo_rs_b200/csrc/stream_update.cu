@@ -422,7 +422,7 @@ namespace {
 
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DevGuard guard(h->device);
     cudaFree(h->S); cudaFree(h->xc); cudaFree(h->g); cudaFree(h->gt); cudaFree(h->pack); cudaFree(h->partial); cudaFree(h->sc);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -512,7 +512,7 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     cudaDeviceProp prop;
     ELL_CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
     if (prop.major < 10) { set_error("libellcuda is built for sm_100a (B200) only"); return ELLCUDA_E_CUDA; }
-    ELL_CUDA_TRY(cudaSetDevice(d->device));
+    ELL_DEVICE_SCOPE(d->device);
     if (d->mq) {  // symmetric input required (see capi.cu)
         const long long n = d->n;
         for (long long i = 0; i < n; ++i)
@@ -565,7 +565,7 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
 
 int ellcuda_clone(ell_handle h, ell_handle* out) {
     if (!h || !out) { set_error("null handle"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     ellcuda_ctx* c = new ellcuda_ctx();
     c->device = h->device; c->n = h->n; c->w = h->w; c->c0 = h->c0;
     c->nseg = h->nseg; c->reduce_mode = h->reduce_mode; c->no_defer = h->no_defer; c->use_parallel = h->use_parallel;
@@ -591,7 +591,7 @@ void ellcuda_destroy(ell_handle h) { free_ctx(h); }
 
 int ellcuda_xc(ell_handle h, double* out) {
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaMemcpyAsync(out, h->xc, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ELLCUDA_OK;
@@ -599,14 +599,14 @@ int ellcuda_xc(ell_handle h, double* out) {
 
 int ellcuda_set_xc(ell_handle h, const double* x) {
     if (!h || !x) { set_error("null argument"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaMemcpyAsync(h->xc, x, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ELLCUDA_OK;
 }
 
 static int read_scal(ell_handle h, Scal* sc) {
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaMemcpyAsync(sc, h->sc, sizeof(Scal), cudaMemcpyDeviceToHost, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ELLCUDA_OK;
@@ -632,7 +632,7 @@ int ellcuda_kappa(ell_handle h, double* out) {
 
 int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row-major
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     Scal sc;
     int rc = read_scal(h, &sc);
     if (rc) return rc;
@@ -653,7 +653,7 @@ int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row
 int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, double beta0, int32_t has_beta1, double beta1) {
     if (!h || !grad_dev) { set_error("null argument"); return ELLCUDA_E_ARG; }
     if (which < ELL_UPDATE_BIAS || which > ELL_UPDATE_Q) { set_error("bad update selector"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     h->which = which;
     h->cut = has_beta1 > 0 ? parallel_cut(beta0, beta1) : single_cut(beta0);
     return enqueue_begin(h, grad_dev);
@@ -661,7 +661,7 @@ int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, do
 
 int ellcuda_update_finish(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
     finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->g, h->gt, h->xc, h->sc, h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode);
     ELL_CUDA_TRY(cudaGetLastError());
@@ -673,7 +673,7 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double 
                    int32_t* out_status) {
     if (!h || !grad_host || !out_status) { set_error("null argument"); return ELLCUDA_E_ARG; }
     if (h->w != h->n) { set_error("ellcuda_update needs a whole-matrix handle; sharded handles use update_begin/finish"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     // stage the gradient in h->g's neighbour: reuse the tail of `partial`? keep it simple: a dedicated async alloc
     double* gdev = nullptr;
     ELL_CUDA_TRY(cudaMallocAsync((void**)&gdev, (size_t)h->n * 8, h->stream));
@@ -692,7 +692,7 @@ int32_t* ellcuda_status_ptr(ell_handle h) { return h ? &h->sc->status : nullptr;
 
 int ellcuda_last_status(ell_handle h, int32_t* out_status) {
     if (!h || !out_status) { set_error("null argument"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     int st = 0;
     ELL_CUDA_TRY(cudaMemcpyAsync(&st, &h->sc->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -702,7 +702,7 @@ int ellcuda_last_status(ell_handle h, int32_t* out_status) {
 
 int ellcuda_set_stream(ell_handle h, void* stream) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
     if (stream) h->stream = (cudaStream_t)stream;
@@ -715,7 +715,7 @@ int ellcuda_set_stream(ell_handle h, void* stream) {
 
 int ellcuda_sync(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
-    ELL_CUDA_TRY(cudaSetDevice(h->device));
+    ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ELLCUDA_OK;
 }

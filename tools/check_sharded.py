@@ -37,6 +37,7 @@ for n, mode in ((1024, 0), (1000, 0), (2048, 4)):
     ok &= bool(np.array_equal(slab, r["mq"][e.lo:e.hi]) if mode == 0 else np.abs(slab - r["mq"][e.lo:e.hi]).max() <= 1e-9)
     print(f"rank {rank}: n={n} mode={mode} rows [{e.lo},{e.hi}) ok={ok}", flush=True)
 prob = W.bowl(1001, n=32, max_iters=300)
+prob.device = local
 out = solve_batch_sharded(prob, batch.solve_batch, rank, world)
 if rank == 0:
     whole = batch.solve_batch(prob)
