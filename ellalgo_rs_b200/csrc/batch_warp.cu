@@ -12,6 +12,8 @@
 // so num_iters and the exit status are identical to the Rust path, not merely close.
 // Drivers: cutting_plane_optim (src/cutting_plane.rs:286-313).
 // Oracles: shifted quadratic bowl (tests/integration_test.rs:90-105), LowpassOracle (src/oracles/lowpass_oracle.rs).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ellcuda {
@@ -22,13 +24,14 @@ constexpr int kWarpScratch = 5 * 32;  // doubles per warp: sx, sg, sgt, srg, sp
 struct WarpCtx {
     int lane;
     int n;
-    double* sx;   // xc
-    double* sg;   // g
-    double* sgt;  // grad_t
-    double* srg;  // ratio * grad_t
-    double* sp;   // g .* grad_t   (oracles may use it as scratch before the update)
+    double* ws;         // per-warp scratch: sx | sg | sgt | srg | sp, 32 doubles each
     const double* tab;  // shared-memory copy of the oracle table (padded rows) or nullptr
     int tab_stride;
+    __device__ __forceinline__ double* sx() const { return ws; }        // xc
+    __device__ __forceinline__ double* sg() const { return ws + 32; }   // g
+    __device__ __forceinline__ double* sgt() const { return ws + 64; }  // grad_t
+    __device__ __forceinline__ double* srg() const { return ws + 96; }  // ratio * grad_t
+    __device__ __forceinline__ double* sp() const { return ws + 128; }  // g .* grad_t (oracle scratch before the update)
 };
 
 template <bool FIXED32>
@@ -57,9 +60,9 @@ struct OrBowl {  // tests/integration_test.rs:90-105
     __device__ bool assess_optim(const WarpCtx& c, double xc, double& gamma, double& g, Cut& cut) {
         const double diff = xc - t;
         g = 2.0 * diff;
-        c.sp[c.lane] = diff * diff;
+        c.sp()[c.lane] = diff * diff;
         __syncwarp();
-        const double f = seq_sum<FIXED32>(c.sp, c.n);
+        const double f = seq_sum<FIXED32>(c.sp(), c.n);
         cut = single_cut(f);
         if (f < gamma) {
             gamma = f;
@@ -70,7 +73,7 @@ struct OrBowl {  // tests/integration_test.rs:90-105
     static constexpr bool kNeedsTable = false;
 };
 
-template <bool FIXED32>
+template <bool FIXED32, int kRowsPerLane>
 struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
     int idx1, idx2, idx3, nwpass, nwstop, mdim, kmax;
     double lp_sq, up_sq, sp_sq, fmax;
@@ -86,65 +89,86 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
         fmax = -INFINITY; kmax = -1;
         (void)c;
     }
-    // spectrum[k].dot(x): sequential over j (src/arr.rs:443-451); x is the broadcast copy in c.sx
-    __device__ __forceinline__ double row_dot(const WarpCtx& c, int k) const {
-        const double* row = c.tab + (long long)k * c.tab_stride;
-        double acc = 0.0;
+    // spectrum[k].dot(x) for the R rows this lane evaluates in one round: each sum is sequential over j
+    // (src/arr.rs:443-451); x is the broadcast copy in c.sx(); the R chains are independent and interleave.
+    template <int R>
+    __device__ __forceinline__ void row_dots(const WarpCtx& c, const int (&k)[R], double (&acc)[R]) const {
+        const double* row[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            row[r] = c.tab + (long long)k[r] * c.tab_stride;
+            acc[r] = 0.0;
+        }
         if constexpr (FIXED32) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-                const double2 x = *reinterpret_cast<const double2*>(c.sx + j);
-                acc += row[j] * x.x;
-                acc += row[j + 1] * x.y;
+                const double2 x = *reinterpret_cast<const double2*>(c.sx() + j);
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] += row[r][j] * x.x;
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] += row[r][j + 1] * x.y;
             }
         } else {
-            for (int j = 0; j < c.n; ++j) acc += row[j] * c.sx[j];
+            for (int j = 0; j < c.n; ++j) {
+                const double x = c.sx()[j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] += row[r][j] * x;
+            }
         }
-        return acc;
     }
     __device__ __forceinline__ double row_elem(const WarpCtx& c, int k) const {
         return c.lane < c.n ? c.tab[(long long)k * c.tab_stride + c.lane] : 0.0;
     }
 
-    // One round-robin band sweep, 32 rows at a time (one per lane), stopping at the first row in traversal order
-    // that violates.  BAND: 0 pass-band (:62-78), 1 stop-band (:83-104), 2 transition band (:106-119).
-    // Returns true when a cut was produced.
-    template <int BAND>
+    // One round-robin band sweep, 32·R rows per round (R per lane; traversal position = base + 32·r + lane), stopping
+    // at the first row in traversal order that violates.  BAND: 0 pass-band (:62-78), 1 stop-band (:83-104),
+    // 2 transition band (:106-119).  Returns true when a cut was produced.
+    template <int BAND, int R>
     __device__ __forceinline__ bool sweep(const WarpCtx& c, int lo, int hi, int& cursor, double& g, Cut& cut) {
         const int len = hi - lo;
         double best_v = -INFINITY;
         int best_c = 0x7fffffff, best_k = -1;
-        for (int base = 0; base < len; base += 32) {
-            const int cidx = base + c.lane;
-            const bool active = cidx < len;
-            int k = cursor + 1 + cidx;
-            if (k >= hi) k -= len;
-            const double val = active ? row_dot(c, k) : 0.0;
-            bool viol;
-            if (BAND == 0) viol = active && (val > up_sq || val < lp_sq);
-            else if (BAND == 1) viol = active && (val > sp_sq || val < 0.0);
-            else viol = active && (val < 0.0);
-            const unsigned mask = __ballot_sync(0xffffffffu, viol);
-            if (mask) {
-                const int first = __ffs(mask) - 1;
-                const int kf = __shfl_sync(0xffffffffu, k, first);
-                const double vf = __shfl_sync(0xffffffffu, val, first);
-                cursor = kf;
-                const double e = row_elem(c, kf);
-                if (BAND == 0) {
-                    if (vf > up_sq) { g = e; cut = parallel_cut(vf - up_sq, vf - lp_sq); }
-                    else { g = -e; cut = parallel_cut(-vf + lp_sq, -vf + up_sq); }
-                } else if (BAND == 1) {
-                    if (vf > sp_sq) { g = e; cut = parallel_cut(vf - sp_sq, vf); }
-                    else { g = -e; cut = parallel_cut(-vf, -vf + sp_sq); }
-                    // fmax/kmax of a partial sweep are never read (reset at the next sweep, :83-84)
-                } else {
-                    g = -e; cut = single_cut(-vf);  // ParallelCut(-val, None)
-                }
-                return true;
+        for (int base = 0; base < len; base += 32 * R) {
+            int k[R];
+            double val[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int cidx = base + 32 * r + c.lane;
+                int kk = cursor + 1 + cidx;
+                if (kk >= hi) kk -= len;
+                k[r] = cidx < len ? kk : lo;      // inactive slots read a valid row and are masked below
             }
-            if (BAND == 1) {  // `if val > fmax` in traversal order = first occurrence of the maximum
-                if (active && val > best_v) { best_v = val; best_c = cidx; best_k = k; }
+            row_dots<R>(c, k, val);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int cidx = base + 32 * r + c.lane;
+                const bool active = cidx < len;
+                bool viol;
+                if (BAND == 0) viol = active && (val[r] > up_sq || val[r] < lp_sq);
+                else if (BAND == 1) viol = active && (val[r] > sp_sq || val[r] < 0.0);
+                else viol = active && (val[r] < 0.0);
+                const unsigned mask = __ballot_sync(0xffffffffu, viol);
+                if (mask) {
+                    const int first = __ffs(mask) - 1;
+                    const int kf = __shfl_sync(0xffffffffu, k[r], first);
+                    const double vf = __shfl_sync(0xffffffffu, val[r], first);
+                    cursor = kf;
+                    const double e = row_elem(c, kf);
+                    if (BAND == 0) {
+                        if (vf > up_sq) { g = e; cut = parallel_cut(vf - up_sq, vf - lp_sq); }
+                        else { g = -e; cut = parallel_cut(-vf + lp_sq, -vf + up_sq); }
+                    } else if (BAND == 1) {
+                        if (vf > sp_sq) { g = e; cut = parallel_cut(vf - sp_sq, vf); }
+                        else { g = -e; cut = parallel_cut(-vf, -vf + sp_sq); }
+                        // fmax/kmax of a partial sweep are never read (reset at the next sweep, :83-84)
+                    } else {
+                        g = -e; cut = single_cut(-vf);  // ParallelCut(-val, None)
+                    }
+                    return true;
+                }
+                if (BAND == 1) {  // `if val > fmax` in traversal order = first occurrence of the maximum
+                    if (active && val[r] > best_v) { best_v = val[r]; best_c = cidx; best_k = k[r]; }
+                }
             }
         }
         // no violation: the cursor has advanced `len` times and sits on the last row visited
@@ -168,11 +192,11 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
     __device__ bool assess_optim(const WarpCtx& c, double xc, double& gamma, double& g, Cut& cut) {  // :137-150
         (void)xc;
         sp_sq = gamma;
-        if (sweep<0>(c, 0, nwpass, idx1, g, cut)) return false;
+        if (sweep<0, kRowsPerLane>(c, 0, nwpass, idx1, g, cut)) return false;
         fmax = -INFINITY; kmax = -1;
-        if (sweep<1>(c, nwstop, mdim, idx3, g, cut)) return false;
-        if (sweep<2>(c, nwpass, nwstop, idx2, g, cut)) return false;
-        const double x0 = c.sx[0];
+        if (sweep<1, kRowsPerLane>(c, nwstop, mdim, idx3, g, cut)) return false;
+        if (sweep<2, kRowsPerLane>(c, nwpass, nwstop, idx2, g, cut)) return false;
+        const double x0 = c.sx()[0];
         if (x0 < 0.0) {  // :123-127
             g = c.lane == 0 ? -1.0 : 0.0;
             cut = single_cut(-x0);
@@ -186,8 +210,8 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
 };
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <class Oracle, bool FIXED32, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) batch_warp_kernel(const BatchArgs a) {
+template <class Oracle, bool FIXED32, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) batch_warp_kernel(const BatchArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -214,8 +238,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) batch_warp_k
     }
     c.tab = tab_s;
     c.tab_stride = tab_stride;
-    double* ws = scratch + warp * kWarpScratch;
-    c.sx = ws; c.sg = ws + 32; c.sgt = ws + 64; c.srg = ws + 96; c.sp = ws + 128;
+    c.ws = scratch + warp * kWarpScratch;
 
     const CalcConsts cc = CalcConsts::make(n, a.use_parallel_cut);
     const bool lane_on = lane < n;
@@ -251,7 +274,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) batch_warp_k
         int exit_status = kExitMaxIt;
 
         for (; niter < a.max_iters; ++niter) {  // cutting_plane_optim, src/cutting_plane.rs:299-311
-            c.sx[lane] = xc;
+            c.sx()[lane] = xc;
             __syncwarp();
             double g = 0.0;
             Cut cut;
@@ -261,25 +284,25 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) batch_warp_k
             const int which = shrunk ? kCentral : kBias;
 
             // ---- Ell::update_core (src/ell.rs:97-137)
-            c.sg[lane] = g;
+            c.sg()[lane] = g;
             __syncwarp();
             double gt = 0.0;
             if constexpr (FIXED32) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const double2 gv = *reinterpret_cast<const double2*>(c.sg + j);
+                    const double2 gv = *reinterpret_cast<const double2*>(c.sg() + j);
                     gt += m[j] * gv.x;
                     gt += m[j + 1] * gv.y;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (j < n) gt += m[j] * c.sg[j];
+                    if (j < n) gt += m[j] * c.sg()[j];
             }
-            c.sp[lane] = g * gt;
-            c.sgt[lane] = gt;
+            c.sp()[lane] = g * gt;
+            c.sgt()[lane] = gt;
             __syncwarp();
-            const double omega = seq_sum<FIXED32>(c.sp, n);
+            const double omega = seq_sum<FIXED32>(c.sp(), n);
             tsq = kappa * omega;
             Rsd r;
             const int status = ell_calc(cc, which, cut, tsq, r);
@@ -288,34 +311,27 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) batch_warp_k
             xc -= rho_over_omega * gt;
             const double ratio = r.sigma / omega;
             const double rg = ratio * gt;
-            c.srg[lane] = rg;
+            c.srg()[lane] = rg;
             __syncwarp();
+            // element (lane, j): hi = max(lane, j) supplies ratio*grad_t, lo = min(lane, j) supplies grad_t
             if constexpr (FIXED32) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const double2 gv = *reinterpret_cast<const double2*>(c.sgt + j);
-                    const double2 rv = *reinterpret_cast<const double2*>(c.srg + j);
-                    {   // element (lane, j): hi = max(lane, j) supplies ratio*grad_t, lo = min supplies grad_t
-                        const bool lower = j <= lane;
-                        const double x = lower ? rg : rv.x;
-                        const double y = lower ? gv.x : gt;
-                        m[j] -= x * y;
-                    }
-                    {
-                        const bool lower = (j + 1) <= lane;
-                        const double x = lower ? rg : rv.y;
-                        const double y = lower ? gv.y : gt;
-                        m[j + 1] -= x * y;
-                    }
+                    const double2 gv = *reinterpret_cast<const double2*>(c.sgt() + j);
+                    const double2 rv = *reinterpret_cast<const double2*>(c.srg() + j);
+                    double u0, u1;
+                    if (j <= lane) u0 = rg * gv.x; else u0 = rv.x * gt;
+                    if (j + 1 <= lane) u1 = rg * gv.y; else u1 = rv.y * gt;
+                    m[j] -= u0;
+                    m[j + 1] -= u1;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (j < n) {
-                        const bool lower = j <= lane;
-                        const double x = lower ? rg : c.srg[j];
-                        const double y = lower ? c.sgt[j] : gt;
-                        m[j] -= x * y;
+                        double u;
+                        if (j <= lane) u = rg * c.sgt()[j]; else u = c.srg()[j] * gt;
+                        m[j] -= u;
                     }
                 }
             }
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1)) batch_warp_k
     }
 }
 
-template <class Oracle, bool FIXED32, int WARPS>
+template <class Oracle, bool FIXED32, int WARPS, int MINB>
 int launch_one(const BatchArgs& a, cudaStream_t s, int sm_count) {
     const int n = a.n;
     size_t smem = (size_t)WARPS * kWarpScratch * sizeof(double);
@@ -355,7 +371,7 @@ int launch_one(const BatchArgs& a, cudaStream_t s, int sm_count) {
         smem += t * sizeof(double);
     }
     if (smem > 227 * 1024) { set_error("oracle table does not fit in shared memory"); return ELLCUDA_E_ARG; }
-    auto kern = batch_warp_kernel<Oracle, FIXED32, WARPS>;
+    auto kern = batch_warp_kernel<Oracle, FIXED32, WARPS, MINB>;
     ELL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     ELL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -369,6 +385,13 @@ int launch_one(const BatchArgs& a, cudaStream_t s, int sm_count) {
     return ELLCUDA_OK;
 }
 
+// ELLCUDA_TUNE=<k> selects an alternative warps-per-CTA / registers-per-thread variant (performance experiments only;
+// every variant computes identical results)
+int tuning_variant() {
+    const char* e = getenv("ELLCUDA_TUNE");
+    return e ? atoi(e) : 0;
+}
+
 }  // namespace
 
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
@@ -380,14 +403,25 @@ int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_
     int rc;
     if (oracle_id == ELL_ORACLE_BOWL) {
         if (!a.params || a.params_width < a.n) { set_error("BOWL needs params[n] = target"); return ELLCUDA_E_ARG; }
-        rc = a.n == 32 ? launch_one<OrBowl<true>, true, 8>(a, s, sm_count) : launch_one<OrBowl<false>, false, 8>(a, s, sm_count);
+        const int v = tuning_variant();
+        if (a.n != 32) rc = launch_one<OrBowl<false>, false, 8, 2>(a, s, sm_count);
+        else if (v == 1) rc = launch_one<OrBowl<true>, true, 6, 2>(a, s, sm_count);   // 164 regs, no spills: 1038 M iter/s
+        // default 8 warps x 2 CTAs (128 regs): 1100 M iter/s; 10x2 875; 12x2 and 16x1 no better
+        else rc = launch_one<OrBowl<true>, true, 8, 2>(a, s, sm_count);
     } else if (oracle_id == ELL_ORACLE_LOWPASS) {
         if (!a.params || a.params_width < 5 || !a.table || a.aux[0] != 15 * a.n || a.table_len < (long long)a.aux[0] * a.n) {
             set_error("LOWPASS needs params[5], the spectrum table and aux[0] = 15*n");
             return ELLCUDA_E_ARG;
         }
-        rc = a.n == 32 ? launch_one<OrLowpass<true>, true, 16>(a, s, sm_count)
-                       : launch_one<OrLowpass<false>, false, 16>(a, s, sm_count);
+        const int v = tuning_variant();
+        // Measured on B200 (tools/probe_tune.py, 16384 problems): rows-per-lane R x warps-per-CTA W ->
+        //   R1W8 402 M iter/s (196 regs, no spills) | R2W8 396 | R3W8 363 | R4W8 317 | R1W16 354 (128 regs, spills) | R1W12 333.
+        // The kernel is bound by shared-memory bandwidth (spectrum rows: 256 B per lane per row), so extra
+        // speculative rows (R>1) cost more than the latency they hide, and 8 warps already saturate the LSU.
+        if (a.n != 32) rc = launch_one<OrLowpass<false, 1>, false, 8, 1>(a, s, sm_count);
+        else if (v == 1) rc = launch_one<OrLowpass<true, 2>, true, 8, 1>(a, s, sm_count);
+        else if (v == 2) rc = launch_one<OrLowpass<true, 1>, true, 16, 1>(a, s, sm_count);
+        else rc = launch_one<OrLowpass<true, 1>, true, 8, 1>(a, s, sm_count);
     } else {
         set_error("oracle not available in the warp-per-problem kernel");
         return ELLCUDA_E_ARG;
