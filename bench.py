@@ -272,7 +272,7 @@ def main():
     large = None
     if not args.skip_large_n:
         n = args.large_n
-        mode = 0 if world == 1 else 8
+        mode = 0 if world == 1 else world    # k row segments keep 256 sweep warps per GPU when the slab has n/P columns
         ell = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local)
         grads = [torch.from_numpy(W.large_n_grad(n, k)).to(dev) for k in range(16)]
         cut = ParallelCut(*W.LARGE_N_CUT)

@@ -25,6 +25,17 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return e == cudaErrorMemoryAllocation ? ELLCUDA_E_OOM : ELLCUDA_E_CUDA;
 }
 
+// cudaMallocAsync's default pool gives memory back to the driver at every synchronisation unless told otherwise;
+// the scratch buffers of consecutive calls would then be re-created each time (hundreds of microseconds).
+void keep_mempool(int dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 namespace {
 
 struct DeviceInfo {
@@ -54,6 +65,7 @@ int device_info(int dev, DeviceInfo** out) {
         if (p.major < 10) { set_error("libellcuda is built for sm_100a (B200) only"); return ELLCUDA_E_CUDA; }
         ELL_DEVICE_SCOPE(dev);
         ELL_CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        keep_mempool(dev);
         d.sm_count = p.multiProcessorCount;
         d.major = p.major;
         d.ok = true;

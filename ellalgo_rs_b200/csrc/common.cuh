@@ -42,6 +42,7 @@ struct BatchArgs {
 };
 
 void set_error(const std::string& msg);
+void keep_mempool(int dev);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define ELL_CUDA_TRY(expr)                                                         \

@@ -12,7 +12,7 @@
 // sum over j, term for term and in the same order; with reduce_mode 0 grad_t and omega are bit-identical to Rust.
 //
 // Kernel shape: a CTA is ONE WARP that owns 64 adjacent columns (2 per lane) and walks down all rows; tiles of
-// 32 rows × 64 columns (16 KB) are staged in shared memory by TMA (cp.async.bulk.tensor.2d, 4-stage mbarrier ring),
+// 64 rows × 64 columns (32 KB) are staged in shared memory by TMA (cp.async.bulk.tensor.2d, 3-stage mbarrier ring),
 // updated in place, and written back by TMA.  Global traffic is therefore fully coalesced 512-byte row segments
 // issued by the copy engine; the lanes only touch shared memory (conflict-free 16-byte accesses).  n=16384 gives
 // 256 such warps (all resident, 2–3 per SM); the sequential accumulation a lane carries costs ~20 cycles per row
@@ -21,6 +21,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -30,10 +32,10 @@ namespace ellcuda {
 namespace {
 
 constexpr int kCols = 64;    // columns per warp (2 per lane)
-constexpr int kRows = 32;    // rows per TMA tile
-constexpr int kStages = 4;   // smem ring depth
-constexpr int kTileBytes = kCols * kRows * 8;
-constexpr int kPackBytes = kRows * 32;  // per tile: {g[i], gt[i], ratio*gt[i], 0} per row
+constexpr int kRowsDefault = 64;    // rows per TMA tile   (measured at n=16384: 64x3 682 us, 32x6 693, 48x4 692,
+constexpr int kStagesDefault = 3;   // smem ring depth      32x4 709, 48x3 753, 32x3 840, 16x8 831, 64x4 1219 [1 CTA/SM])
+constexpr int kRowsMax = 64;
+// per tile: kCols*ROWS*8 bytes of M and ROWS*32 bytes of pack {g[i], gt[i], ratio*gt[i], 0}
 
 struct Scal {  // device-resident scalars of the Ell (src/ell.rs:9-16) + the deferred rank-1
     double kappa;
@@ -147,10 +149,12 @@ __device__ __forceinline__ void tile_rows(double2* __restrict__ tile, const doub
     }
 }
 
-template <bool PENDING, bool SCALE>
+template <int kRows, int kStages, bool PENDING, bool SCALE>
 __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const double4* __restrict__ pack, double* __restrict__ out,
                                            long long w, long long row_lo, long long row_hi, long long c_glob0, double scale,
                                            unsigned char* smem_raw) {
+    constexpr int kTileBytes = kCols * kRows * 8;
+    constexpr int kPackBytes = kRows * 32;
     // smem: [kStages tiles][kStages packs][kStages mbarriers]
     double2* tiles = reinterpret_cast<double2*>(smem_raw);
     double4* packs = reinterpret_cast<double4*>(smem_raw + kStages * kTileBytes);
@@ -227,6 +231,7 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const double4
 }
 
 // grid = (column blocks, row segments); block = 32 threads.
+template <int kRows, int kStages>
 __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUtensorMap map, const double4* __restrict__ pack,
                                                    const Scal* __restrict__ sc, double* __restrict__ partial, long long ld_part,
                                                    long long n, long long w, long long c_glob0, int nseg) {
@@ -245,9 +250,9 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     }
     const int pending = sc->pending;
     const double scale = sc->scale;
-    if (!pending) sweep_body<false, false>(&map, pack, out, w, row_lo, row_hi, c_glob0, 1.0, smem_raw);
-    else if (scale == 1.0) sweep_body<true, false>(&map, pack, out, w, row_lo, row_hi, c_glob0, 1.0, smem_raw);
-    else sweep_body<true, true>(&map, pack, out, w, row_lo, row_hi, c_glob0, scale, smem_raw);
+    if (!pending) sweep_body<kRows, kStages, false, false>(&map, pack, out, w, row_lo, row_hi, c_glob0, 1.0, smem_raw);
+    else if (scale == 1.0) sweep_body<kRows, kStages, true, false>(&map, pack, out, w, row_lo, row_hi, c_glob0, 1.0, smem_raw);
+    else sweep_body<kRows, kStages, true, true>(&map, pack, out, w, row_lo, row_hi, c_glob0, scale, smem_raw);
 }
 
 // grad_t[c_glob0 + c] = sum over row segments, in segment order (one segment: a copy).
@@ -367,7 +372,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols, long long ld) {
+int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols, long long ld, int box_rows) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -378,10 +383,16 @@ int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)kCols, (cuuint32_t)kRows};
+    const cuuint32_t box[2] = {(cuuint32_t)kCols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("ELLCUDA_L2PROMO")) {   // performance experiments
+        const int v = atoi(e);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         return ELLCUDA_E_CUDA;
@@ -389,7 +400,7 @@ int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols
     return ELLCUDA_OK;
 }
 
-constexpr size_t kSweepSmem = (size_t)kStages * (kTileBytes + kPackBytes) + kStages * 8 + 128;
+constexpr size_t sweep_smem(int rows, int stages) { return (size_t)stages * (kCols * rows * 8 + rows * 32) + stages * 8 + 128; }
 
 }  // namespace
 }  // namespace ellcuda
@@ -399,11 +410,14 @@ struct ellcuda_ctx {
     int device = 0;
     long long n = 0, w = 0, c0 = 0, ld = 0, npad = 0, ld_part = 0;
     int nseg = 1, reduce_mode = 0, no_defer = 0, use_parallel = 1;
+    int tile_rows = ellcuda::kRowsDefault, stages = ellcuda::kStagesDefault;   // sweep tile shape (ELLCUDA_SWEEP=rows,stages)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     double* S = nullptr;        // n × ld, column block [c0, c0+w) of the symmetric matrix
     double* xc = nullptr;       // n
     double* g = nullptr;        // n, gradient of the update in flight
+    double* gstage = nullptr;   // n, landing buffer for host gradients (ellcuda_update)
+    int* status_host = nullptr; // pinned, CutStatus read-back
     double* gt = nullptr;       // n, grad_t (full length; a rank writes [c0, c0+w))
     double4* pack = nullptr;    // npad + kCols + 2 (tail stays zero)
     double* partial = nullptr;  // nseg × ld_part
@@ -423,7 +437,7 @@ namespace {
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
     DevGuard guard(h->device);
-    cudaFree(h->S); cudaFree(h->xc); cudaFree(h->g); cudaFree(h->gt); cudaFree(h->pack); cudaFree(h->partial); cudaFree(h->sc);
+    cudaFree(h->S); cudaFree(h->xc); cudaFree(h->g); cudaFree(h->gstage); cudaFreeHost(h->status_host); cudaFree(h->gt); cudaFree(h->pack); cudaFree(h->partial); cudaFree(h->sc);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -433,11 +447,21 @@ void free_ctx(ellcuda_ctx* h) {
 int alloc_ctx(ellcuda_ctx* h) {
     const long long n = h->n;
     h->ld = (h->w + 1) & ~1LL;  // TMA needs a 16-byte row pitch
-    h->npad = (n + kRows - 1) / kRows * kRows + kRows;
+    if (const char* e = getenv("ELLCUDA_SWEEP")) {   // performance experiments: "rows,stages"
+        int r = 0, st = 0;
+        if (sscanf(e, "%d,%d", &r, &st) == 2 && (r == 16 || r == 32 || r == 48 || r == 64) && (st == 3 || st == 4 || st == 6 || st == 8)) {
+            h->tile_rows = r;
+            h->stages = st;
+        }
+    }
+    h->npad = (n + kRowsMax - 1) / kRowsMax * kRowsMax + kRowsMax;
     h->ld_part = (h->w + kCols - 1) / kCols * kCols;
     ELL_CUDA_TRY(cudaMalloc(&h->S, (size_t)n * h->ld * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->xc, (size_t)n * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->g, (size_t)n * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->gstage, (size_t)n * 8));
+    ELL_CUDA_TRY(cudaMallocHost(&h->status_host, sizeof(int)));
+    keep_mempool(h->device);
     ELL_CUDA_TRY(cudaMalloc(&h->gt, (size_t)n * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->pack, (size_t)(h->npad + kCols + 2) * 32));
     ELL_CUDA_TRY(cudaMalloc(&h->partial, (size_t)h->nseg * h->ld_part * 8));
@@ -447,19 +471,43 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMemset(h->pack, 0, (size_t)(h->npad + kCols + 2) * 32));
     ELL_CUDA_TRY(cudaMemset(h->gt, 0, (size_t)n * 8));
     ELL_CUDA_TRY(cudaMemset(h->g, 0, (size_t)n * 8));
-    int rc = make_tensor_map(&h->map, h->S, n, h->w, h->ld);
+    int rc = make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
-        attr_set = true;
-    }
     return ELLCUDA_OK;
 }
 
 // begin = pack + sweep + combine.  g_dev may be null (flush: applies the pending rank-1 only).
+template <int R, int ST>
+int launch_sweep_t(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {
+    static bool attr_set = false;   // per instantiation
+    constexpr size_t smem = sweep_smem(R, ST);
+    if (!attr_set) {
+        ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    sweep_kernel<R, ST><<<grid, 32, smem, s>>>(h->map, h->pack, h->sc, h->partial, h->ld_part, h->n, h->w, h->c0, h->nseg);
+    return ELLCUDA_OK;
+}
+
+int launch_sweep(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {
+    const int key = h->tile_rows * 100 + h->stages;
+    switch (key) {
+        case 1604: return launch_sweep_t<16, 4>(h, grid, s);
+        case 1606: return launch_sweep_t<16, 6>(h, grid, s);
+        case 1608: return launch_sweep_t<16, 8>(h, grid, s);
+        case 3203: return launch_sweep_t<32, 3>(h, grid, s);
+        case 3206: return launch_sweep_t<32, 6>(h, grid, s);
+        case 4804: return launch_sweep_t<48, 4>(h, grid, s);
+        case 4803: return launch_sweep_t<48, 3>(h, grid, s);
+        case 6404: return launch_sweep_t<64, 4>(h, grid, s);
+        case 3204: return launch_sweep_t<32, 4>(h, grid, s);
+        default: return launch_sweep_t<64, 3>(h, grid, s);
+    }
+}
+
 int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
     cudaStream_t s = h->stream;
+    int rc_launch = 0;
     const int thr = 256;
     pack_kernel<<<(unsigned)((h->npad + thr - 1) / thr), thr, 0, s>>>(g_dev, h->g, h->gt, h->sc, h->pack, h->n, h->npad);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -467,7 +515,7 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
     const bool rec = h->timing && cap == cudaStreamCaptureStatusNone;
     if (rec) ELL_CUDA_TRY(cudaEventRecord(h->ev0, s));
     dim3 grid((unsigned)(h->ld_part / kCols), (unsigned)h->nseg);
-    sweep_kernel<<<grid, 32, kSweepSmem, s>>>(h->map, h->pack, h->sc, h->partial, h->ld_part, h->n, h->w, h->c0, h->nseg);
+    if ((rc_launch = launch_sweep(h, grid, s))) return rc_launch;
     if (rec) { ELL_CUDA_TRY(cudaEventRecord(h->ev1, s)); h->timed = true; }
     combine_kernel<<<(unsigned)((h->w + thr - 1) / thr), thr, 0, s>>>(h->partial, h->ld_part, h->nseg, h->gt, h->w, h->c0);
     ELL_CUDA_TRY(cudaGetLastError());
@@ -674,14 +722,8 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double 
     if (!h || !grad_host || !out_status) { set_error("null argument"); return ELLCUDA_E_ARG; }
     if (h->w != h->n) { set_error("ellcuda_update needs a whole-matrix handle; sharded handles use update_begin/finish"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
-    // stage the gradient in h->g's neighbour: reuse the tail of `partial`? keep it simple: a dedicated async alloc
-    double* gdev = nullptr;
-    ELL_CUDA_TRY(cudaMallocAsync((void**)&gdev, (size_t)h->n * 8, h->stream));
-    cudaError_t e = cudaMemcpyAsync(gdev, grad_host, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream);
-    int rc = ELLCUDA_OK;
-    if (e == cudaSuccess) rc = ellcuda_update_begin(h, which, gdev, beta0, has_beta1, beta1);
-    cudaFreeAsync(gdev, h->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "grad upload", __FILE__, __LINE__);
+    ELL_CUDA_TRY(cudaMemcpyAsync(h->gstage, grad_host, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = ellcuda_update_begin(h, which, h->gstage, beta0, has_beta1, beta1);
     if (rc) return rc;
     if ((rc = ellcuda_update_finish(h))) return rc;
     return ellcuda_last_status(h, out_status);
@@ -693,10 +735,9 @@ int32_t* ellcuda_status_ptr(ell_handle h) { return h ? &h->sc->status : nullptr;
 int ellcuda_last_status(ell_handle h, int32_t* out_status) {
     if (!h || !out_status) { set_error("null argument"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
-    int st = 0;
-    ELL_CUDA_TRY(cudaMemcpyAsync(&st, &h->sc->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ELL_CUDA_TRY(cudaMemcpyAsync(h->status_host, &h->sc->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    *out_status = st;
+    *out_status = *h->status_host;
     return ELLCUDA_OK;
 }
 

@@ -27,3 +27,14 @@ for mode in [int(a) for a in sys.argv[2:]] or [0]:
     print(f"n={n} mode={mode}: {dt*1e3:.3f} ms/update (loop incl. event syncs), sweep median {sw:.3f} ms min {min(sweeps):.3f} "
           f"→ {16.0*n*n/sw/1e6:.0f} GB/s algorithmic; status={e.last_status()} kappa={e.kappa:.6g}", flush=True)
     del e
+
+# host-gradient path (SearchSpace::update_bias_cut through ellcuda_update): H2D + 4 kernels + status read-back per call
+e = Ell.new_with_scalar(1.0, np.zeros(n))
+hg = [torch.from_numpy(W.large_n_grad(n, k)).pin_memory().numpy() for k in range(8)]
+for k in range(5):
+    e.update_bias_cut((hg[k % 8], cut))
+t0 = time.perf_counter()
+for k in range(30):
+    e.update_bias_cut((hg[k % 8], cut))
+dt = (time.perf_counter() - t0) / 30
+print(f"n={n} host-gradient update: {dt*1e3:.3f} ms/update → {16.0*n*n/dt/1e9:.0f} GB/s algorithmic", flush=True)
