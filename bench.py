@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--per-gpu", type=int, default=PER_GPU)
     ap.add_argument("--large-n", type=int, default=LARGE_N)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,7 +274,7 @@ def main():
     if not args.skip_large_n:
         n = args.large_n
         mode = 0 if world == 1 else world    # k row segments keep 256 sweep warps per GPU when the slab has n/P columns
-        ell = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local)
+        ell = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local, exchange=args.exchange)
         grads = [torch.from_numpy(W.large_n_grad(n, k)).to(dev) for k in range(16)]
         cut = ParallelCut(*W.LARGE_N_CUT)
         for k in range(LARGE_WARMUP):
@@ -302,7 +303,7 @@ def main():
             "value": gbs, "unit": "GB/s", "updates_per_s": LARGE_UPDATES / t_large, "ms_per_update": 1e3 * t_large / LARGE_UPDATES,
             "n": n, "updates": LARGE_UPDATES, "warmup": LARGE_WARMUP, "scaling": "strong", "reduce_mode": mode,
             "last_status": status, "gpu_launches": int(l_launch),
-            "collective": None if world == 1 else "NCCL all_gather_into_tensor(grad_t, n*8 bytes) per update",
+            "collective": None if world == 1 else f"{ell.exchange_kind}: grad_t slabs (n*8 bytes total) " + ("stored into every peer's block over NVLink by the kernel that completes them; finish waits on device flags" if ell.exchange_kind == "p2p" else "NCCL all_gather_into_tensor per update"),
             "roofline": {"bound": "hbm", "kernel": "sweep_kernel (fused deferred rank-1 + GEMV, TMA-staged)",
                          "achieved": slab_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": slab_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,

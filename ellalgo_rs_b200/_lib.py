@@ -17,7 +17,8 @@ EXPORTS = [
     "ellcuda_batch_solve", "ellcuda_last_launch_count", "ellcuda_lowpass_table", "ellcuda_lowpass_band_edge",
     "ellcuda_create", "ellcuda_clone", "ellcuda_destroy", "ellcuda_xc", "ellcuda_set_xc", "ellcuda_tsq",
     "ellcuda_kappa", "ellcuda_get_mq", "ellcuda_update", "ellcuda_update_begin", "ellcuda_update_finish",
-    "ellcuda_grad_t_ptr", "ellcuda_status_ptr", "ellcuda_last_status", "ellcuda_set_stream", "ellcuda_sync",
+    "ellcuda_grad_t_ptr", "ellcuda_exchange_export", "ellcuda_exchange_attach", "ellcuda_exchange_attach_ptrs",
+    "ellcuda_exchange_block_ptr", "ellcuda_status_ptr", "ellcuda_last_status", "ellcuda_set_stream", "ellcuda_sync",
     "ellcuda_set_timing", "ellcuda_last_sweep_ms", "ellcuda_handle_launch_count",
     "ellcuda_math_probe", "ellcuda_last_error", "ellcuda_version", "ellcuda_device_count",
 ]
@@ -86,6 +87,14 @@ def lib():
         L.ellcuda_update_finish.restype = C.c_int
         L.ellcuda_grad_t_ptr.argtypes = [H]
         L.ellcuda_grad_t_ptr.restype = C.c_void_p
+        L.ellcuda_exchange_export.argtypes = [H, C.c_void_p]
+        L.ellcuda_exchange_export.restype = C.c_int
+        L.ellcuda_exchange_attach.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
+        L.ellcuda_exchange_attach.restype = C.c_int
+        L.ellcuda_exchange_attach_ptrs.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
+        L.ellcuda_exchange_attach_ptrs.restype = C.c_int
+        L.ellcuda_exchange_block_ptr.argtypes = [H]
+        L.ellcuda_exchange_block_ptr.restype = C.c_void_p
         L.ellcuda_status_ptr.argtypes = [H]
         L.ellcuda_status_ptr.restype = C.c_void_p
         L.ellcuda_last_status.argtypes = [H, _pi]

@@ -265,17 +265,70 @@ __global__ void combine_kernel(const double* __restrict__ partial, long long ld_
     gt[c_glob0 + c] = acc;
 }
 
+// Peer exchange (row-sharded handles attached with ellcuda_exchange_attach): the kernel that completes this rank's
+// slab of grad_t stores it straight into EVERY rank's exchange block over NVLink (peer pointers), then publishes the
+// update's epoch in each peer's flag word; `finish_kernel` on every rank waits for all P flags.  No NCCL call, no host
+// involvement.  The block holds two grad_t buffers (epoch parity) so that a rank one update ahead never overwrites
+// data a slower rank still reads (see the ordering argument in DESIGN.md §5).
+constexpr int kMaxRanks = 16;
+struct PeerTable {
+    double* gt[kMaxRanks];                  // peer r's grad_t buffer for the current parity
+    unsigned long long* flag[kMaxRanks];    // peer r's flag word for THIS rank as source
+    int nranks;
+};
+
+__global__ void __launch_bounds__(1024) combine_push_kernel(const double* __restrict__ partial, long long ld_part, int nseg,
+                                                            long long w, long long c_glob0, PeerTable pt,
+                                                            unsigned long long epoch) {
+    for (long long c = threadIdx.x; c < w; c += blockDim.x) {
+        double acc = partial[c];
+        for (int s = 1; s < nseg; ++s) acc += partial[(long long)s * ld_part + c];
+        for (int r = 0; r < pt.nranks; ++r) pt.gt[r][c_glob0 + c] = acc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pt.nranks) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pt.flag[threadIdx.x]), "l"(epoch) : "memory");
+    }
+}
+
+// returns false on timeout (~2 s) so that a lost peer cannot hang the GPU
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long epoch) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= epoch) return true;
+        if (clock64() - t0 > 4000000000LL) return false;
+        __nanosleep(200);
+    }
+}
+
 // omega, tsq, EllCalc, xc, kappa — one CTA, identical on every rank (src/ell.rs:103-115, 130-135).
 constexpr int kFinThreads = 1024;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)
-__global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, const double* __restrict__ gt,
+__global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, const double* gt,
                                                              double* __restrict__ xc, Scal* __restrict__ sc, long long n,
-                                                             CalcConsts cc, int which, Cut cut, int no_defer, int reduce_mode) {
+                                                             CalcConsts cc, int which, Cut cut, int no_defer, int reduce_mode,
+                                                             const unsigned long long* wait_flags, int wait_n,
+                                                             unsigned long long epoch) {
     __shared__ double prod[kFinChunk];
     __shared__ double s_omega;
     __shared__ double s_roo;
     __shared__ int s_status;
+    __shared__ int s_timeout;
     const int tid = threadIdx.x;
+    if (wait_n > 0) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
+        if (tid == 0) s_timeout = 0;
+        __syncthreads();
+        if (tid < wait_n && !wait_flag(wait_flags + tid, epoch)) s_timeout = 1;
+        __syncthreads();
+        if (s_timeout) {
+            if (tid == 0) { sc->status = kUnknown; sc->pending = 0; }
+            return;
+        }
+    }
     if (reduce_mode == 0) {
         // grad.dot(&grad_t): products in parallel, the sum strictly left to right (src/arr.rs:443-451)
         double acc = 0.0;
@@ -400,6 +453,8 @@ int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols
     return ELLCUDA_OK;
 }
 
+inline size_t xblk_bytes(long long n) { return (size_t)2 * n * 8 + kMaxRanks * 8; }
+inline unsigned long long* xblk_flags(double* blk, long long n) { return reinterpret_cast<unsigned long long*>(blk + 2 * n); }
 constexpr size_t sweep_smem(int rows, int stages) { return (size_t)stages * (kCols * rows * 8 + rows * 32) + stages * 8 + 128; }
 
 }  // namespace
@@ -418,7 +473,12 @@ struct ellcuda_ctx {
     double* g = nullptr;        // n, gradient of the update in flight
     double* gstage = nullptr;   // n, landing buffer for host gradients (ellcuda_update)
     int* status_host = nullptr; // pinned, CutStatus read-back
-    double* gt = nullptr;       // n, grad_t (full length; a rank writes [c0, c0+w))
+    double* xblk = nullptr;     // exchange block: grad_t[2][n] then kMaxRanks flag words (IPC-shareable cudaMalloc)
+    double* gt = nullptr;       // n, current grad_t buffer inside xblk (full length; a rank writes [c0, c0+w))
+    unsigned long long epoch = 0;            // updates begun (selects the buffer parity when peers are attached)
+    int nranks = 0, rank = 0;                // > 0 once ellcuda_exchange_attach* succeeded
+    double* peer_blk[ellcuda::kMaxRanks] = {};   // every rank's exchange block as mapped in this process
+    bool peer_opened[ellcuda::kMaxRanks] = {};   // mapped by cudaIpcOpenMemHandle (must be closed)
     double4* pack = nullptr;    // npad + kCols + 2 (tail stays zero)
     double* partial = nullptr;  // nseg × ld_part
     ellcuda::Scal* sc = nullptr;
@@ -437,7 +497,10 @@ namespace {
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
     DevGuard guard(h->device);
-    cudaFree(h->S); cudaFree(h->xc); cudaFree(h->g); cudaFree(h->gstage); cudaFreeHost(h->status_host); cudaFree(h->gt); cudaFree(h->pack); cudaFree(h->partial); cudaFree(h->sc);
+    cudaFree(h->S); cudaFree(h->xc); cudaFree(h->g); cudaFree(h->gstage); cudaFreeHost(h->status_host); cudaFree(h->pack); cudaFree(h->partial); cudaFree(h->sc);
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (h->peer_opened[r] && h->peer_blk[r]) cudaIpcCloseMemHandle(h->peer_blk[r]);
+    cudaFree(h->xblk);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -462,21 +525,21 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMalloc(&h->gstage, (size_t)n * 8));
     ELL_CUDA_TRY(cudaMallocHost(&h->status_host, sizeof(int)));
     keep_mempool(h->device);
-    ELL_CUDA_TRY(cudaMalloc(&h->gt, (size_t)n * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->xblk, xblk_bytes(n)));
+    ELL_CUDA_TRY(cudaMemset(h->xblk, 0, xblk_bytes(n)));
+    h->gt = h->xblk;
     ELL_CUDA_TRY(cudaMalloc(&h->pack, (size_t)(h->npad + kCols + 2) * 32));
     ELL_CUDA_TRY(cudaMalloc(&h->partial, (size_t)h->nseg * h->ld_part * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->sc, sizeof(Scal)));
     ELL_CUDA_TRY(cudaEventCreate(&h->ev0));
     ELL_CUDA_TRY(cudaEventCreate(&h->ev1));
     ELL_CUDA_TRY(cudaMemset(h->pack, 0, (size_t)(h->npad + kCols + 2) * 32));
-    ELL_CUDA_TRY(cudaMemset(h->gt, 0, (size_t)n * 8));
     ELL_CUDA_TRY(cudaMemset(h->g, 0, (size_t)n * 8));
     int rc = make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows);
     if (rc) return rc;
     return ELLCUDA_OK;
 }
 
-// begin = pack + sweep + combine.  g_dev may be null (flush: applies the pending rank-1 only).
 template <int R, int ST>
 int launch_sweep_t(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {
     static bool attr_set = false;   // per instantiation
@@ -489,27 +552,31 @@ int launch_sweep_t(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {
     return ELLCUDA_OK;
 }
 
-int launch_sweep(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {
+int launch_sweep(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {   // tile rows x ring depth (ELLCUDA_SWEEP, experiments)
     const int key = h->tile_rows * 100 + h->stages;
     switch (key) {
-        case 1604: return launch_sweep_t<16, 4>(h, grid, s);
-        case 1606: return launch_sweep_t<16, 6>(h, grid, s);
         case 1608: return launch_sweep_t<16, 8>(h, grid, s);
-        case 3203: return launch_sweep_t<32, 3>(h, grid, s);
+        case 3204: return launch_sweep_t<32, 4>(h, grid, s);
         case 3206: return launch_sweep_t<32, 6>(h, grid, s);
         case 4804: return launch_sweep_t<48, 4>(h, grid, s);
-        case 4803: return launch_sweep_t<48, 3>(h, grid, s);
-        case 6404: return launch_sweep_t<64, 4>(h, grid, s);
-        case 3204: return launch_sweep_t<32, 4>(h, grid, s);
         default: return launch_sweep_t<64, 3>(h, grid, s);
     }
 }
 
+// begin = pack + sweep + combine (+ push to peers).  g_dev may be null (flush: applies the pending rank-1 only).
 int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
     cudaStream_t s = h->stream;
     int rc_launch = 0;
     const int thr = 256;
-    pack_kernel<<<(unsigned)((h->npad + thr - 1) / thr), thr, 0, s>>>(g_dev, h->g, h->gt, h->sc, h->pack, h->n, h->npad);
+    const bool flush = g_dev == nullptr;
+    const bool peers = h->nranks > 0 && !flush;
+    // with peers attached grad_t alternates between the block's two buffers: `h->gt` still names the previous update's
+    const double* gt_prev = h->gt;
+    if (peers) {
+        h->epoch += 1;
+        h->gt = h->xblk + (h->epoch & 1) * h->n;
+    }
+    pack_kernel<<<(unsigned)((h->npad + thr - 1) / thr), thr, 0, s>>>(g_dev, h->g, gt_prev, h->sc, h->pack, h->n, h->npad);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cap);
     const bool rec = h->timing && cap == cudaStreamCaptureStatusNone;
@@ -517,9 +584,19 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
     dim3 grid((unsigned)(h->ld_part / kCols), (unsigned)h->nseg);
     if ((rc_launch = launch_sweep(h, grid, s))) return rc_launch;
     if (rec) { ELL_CUDA_TRY(cudaEventRecord(h->ev1, s)); h->timed = true; }
-    combine_kernel<<<(unsigned)((h->w + thr - 1) / thr), thr, 0, s>>>(h->partial, h->ld_part, h->nseg, h->gt, h->w, h->c0);
+    if (peers) {
+        PeerTable pt;
+        pt.nranks = h->nranks;
+        for (int r = 0; r < h->nranks; ++r) {
+            pt.gt[r] = h->peer_blk[r] + (h->epoch & 1) * h->n;
+            pt.flag[r] = xblk_flags(h->peer_blk[r], h->n) + h->rank;
+        }
+        combine_push_kernel<<<1, 1024, 0, s>>>(h->partial, h->ld_part, h->nseg, h->w, h->c0, pt, h->epoch);
+    } else if (!flush) {
+        combine_kernel<<<(unsigned)((h->w + thr - 1) / thr), thr, 0, s>>>(h->partial, h->ld_part, h->nseg, h->gt, h->w, h->c0);
+    }
     ELL_CUDA_TRY(cudaGetLastError());
-    h->launches += 3;
+    h->launches += flush ? 2 : 3;
     return ELLCUDA_OK;
 }
 
@@ -627,7 +704,7 @@ int ellcuda_clone(ell_handle h, ell_handle* out) {
     e = cudaMemcpyAsync(c->S, h->S, (size_t)n * h->ld * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->xc, h->xc, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->g, h->g, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->gt, h->gt, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->gt, h->gt, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);   // the clone is detached from peers
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->sc, h->sc, sizeof(Scal), cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { free_ctx(c); return cuda_fail(e, "ellcuda_clone copy", __FILE__, __LINE__); }
@@ -711,7 +788,9 @@ int ellcuda_update_finish(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
     const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
-    finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->g, h->gt, h->xc, h->sc, h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode);
+    const bool peers = h->nranks > 0;
+    finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->g, h->gt, h->xc, h->sc, h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode,
+                                                    peers ? xblk_flags(h->xblk, h->n) : nullptr, peers ? h->nranks : 0, h->epoch);
     ELL_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     return ELLCUDA_OK;
@@ -738,6 +817,63 @@ int ellcuda_last_status(ell_handle h, int32_t* out_status) {
     ELL_CUDA_TRY(cudaMemcpyAsync(h->status_host, &h->sc->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     *out_status = *h->status_host;
+    return ELLCUDA_OK;
+}
+
+int ellcuda_exchange_export(ell_handle h, void* handle_out) {
+    if (!h || !handle_out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    ELL_DEVICE_SCOPE(h->device);
+    cudaIpcMemHandle_t ipc;
+    static_assert(sizeof(ipc) == ELLCUDA_IPC_HANDLE_BYTES, "IPC handle size");
+    ELL_CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->xblk));
+    memcpy(handle_out, &ipc, sizeof ipc);
+    return ELLCUDA_OK;
+}
+
+void* ellcuda_exchange_block_ptr(ell_handle h) { return h ? h->xblk : nullptr; }
+
+static int attach_common(ell_handle h, int32_t nranks, int32_t rank) {
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) { set_error("bad nranks/rank"); return ELLCUDA_E_ARG; }
+    if (h->nranks > 0) { set_error("exchange already attached"); return ELLCUDA_E_ARG; }
+    ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ELLCUDA_OK;
+}
+
+int ellcuda_exchange_attach_ptrs(ell_handle h, int32_t nranks, int32_t rank, void* const* blocks) {
+    if (!h || !blocks) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    ELL_DEVICE_SCOPE(h->device);
+    int rc = attach_common(h, nranks, rank);
+    if (rc) return rc;
+    for (int r = 0; r < nranks; ++r) {
+        h->peer_blk[r] = r == rank ? h->xblk : (double*)blocks[r];
+        if (!h->peer_blk[r]) { set_error("null peer block"); return ELLCUDA_E_ARG; }
+    }
+    h->nranks = nranks; h->rank = rank;
+    return ELLCUDA_OK;
+}
+
+int ellcuda_exchange_attach(ell_handle h, int32_t nranks, int32_t rank, const void* handles) {
+    if (!h || !handles) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    ELL_DEVICE_SCOPE(h->device);
+    int rc = attach_common(h, nranks, rank);
+    if (rc) return rc;
+    const char* hb = (const char*)handles;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { h->peer_blk[r] = h->xblk; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, hb + (size_t)r * ELLCUDA_IPC_HANDLE_BYTES, sizeof ipc);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q)
+                if (h->peer_opened[q]) { cudaIpcCloseMemHandle(h->peer_blk[q]); h->peer_opened[q] = false; h->peer_blk[q] = nullptr; }
+            cuda_fail(e, "cudaIpcOpenMemHandle", __FILE__, __LINE__);
+            return ELLCUDA_E_COMM;
+        }
+        h->peer_blk[r] = (double*)p;
+        h->peer_opened[r] = true;
+    }
+    h->nranks = nranks; h->rank = rank;
     return ELLCUDA_OK;
 }
 

@@ -161,6 +161,24 @@ class Ell:
     def grad_t_view(self) -> _DevVec:
         return _DevVec(lib().ellcuda_grad_t_ptr(self._h), self.n, self)
 
+    # ---- peer exchange over NVLink (include/ellcuda.h: ellcuda_exchange_*)
+    def exchange_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib().ellcuda_exchange_export(self._h, buf))
+        return buf.raw
+
+    def exchange_attach(self, handles: list, rank: int):
+        """handles[r] = exchange_export() of rank r (any order of arrival; own entry is ignored)"""
+        blob = b"".join(handles)
+        check(lib().ellcuda_exchange_attach(self._h, len(handles), rank, blob))
+
+    def exchange_block_ptr(self) -> int:
+        return lib().ellcuda_exchange_block_ptr(self._h)
+
+    def exchange_attach_ptrs(self, blocks: list, rank: int):
+        arr = (C.c_void_p * len(blocks))(*blocks)
+        check(lib().ellcuda_exchange_attach_ptrs(self._h, len(blocks), rank, arr))
+
     def set_stream(self, stream: int):
         check(lib().ellcuda_set_stream(self._h, stream))
 

@@ -48,10 +48,12 @@ class ShardedEll:
     """Row-sharded `Ell` for large n: SearchSpace semantics of src/ell.rs with M split over the ranks of `group`.
 
     update(which, grad_dev, cut): sweep own slab (fused deferred rank-1 + GEMV) -> allgather(grad_t) -> finish.
-    All ranks pass the same gradient (device tensor of n doubles) and end with identical xc / kappa / tsq."""
+    All ranks pass the same gradient (device tensor of n doubles) and end with identical xc / kappa / tsq.
+    With exchange="p2p" (default) the allgather is fused into the kernel that completes the slab: it stores straight
+    into every peer's exchange block over NVLink and `finish` waits on device-side flags."""
 
     def __init__(self, kappa, xc, *, mq=None, diag=None, no_defer_trick=False, use_parallel_cut=True, reduce_mode=0,
-                 device=None, group=None):
+                 device=None, group=None, exchange="p2p"):
         import torch
         import torch.distributed as dist
         from .ell import Ell
@@ -69,11 +71,19 @@ class ShardedEll:
         self.ell.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
         self.grad_t = torch.as_tensor(self.ell.grad_t_view(), device=f"cuda:{self.device}")
         self.even = n % self.world == 0
+        # exchange of the grad_t slabs: "p2p" = stores into every peer's block from the producing kernel over NVLink
+        # (CUDA IPC, no collective call per update); "nccl" = all_gather_into_tensor on torch's stream
+        self.exchange_kind = exchange if self.world > 1 else "none"
+        if self.exchange_kind == "p2p":
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.ell.exchange_export(), group=group)
+            self.ell.exchange_attach(handles, self.rank)
+            dist.barrier(group=group)
 
     def exchange(self):
         """allgather of grad_t slabs, in place (C1 of SURVEY.md §2)"""
-        if self.world == 1:
-            return
+        if self.exchange_kind != "nccl":
+            return            # p2p: the begin kernels already pushed the slab to every peer
         dist = self._dist
         if self.even:
             dist.all_gather_into_tensor(self.grad_t, self.grad_t[self.lo:self.hi], group=self.group)

@@ -216,7 +216,20 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host,
 int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev,
                          double beta0, int32_t has_beta1, double beta1);
 int ellcuda_update_finish(ell_handle h);
-double*  ellcuda_grad_t_ptr(ell_handle h);   /* device, n doubles                          */
+double*  ellcuda_grad_t_ptr(ell_handle h);   /* device, n doubles (the buffer of the most recent begin)   */
+
+/* Peer exchange over NVLink without NCCL (one process per GPU).  Every rank exports its exchange block
+ * (ELLCUDA_IPC_HANDLE_BYTES opaque bytes, a CUDA IPC handle), the P handles are gathered by any means
+ * (e.g. torch.distributed.all_gather_object) and attached; from then on ellcuda_update_begin stores this rank's
+ * slab of grad_t directly into every rank's block from the kernel that produces it, and ellcuda_update_finish
+ * waits (on the device) until all P slabs have arrived — no collective call between begin and finish.
+ * attach_ptrs takes block pointers already valid in this process (ellcuda_exchange_block_ptr of handles living in the
+ * same process; used to emulate ranks on one GPU, all on ONE stream, begin for every rank before any finish).     */
+#define ELLCUDA_IPC_HANDLE_BYTES 64
+int   ellcuda_exchange_export(ell_handle h, void* handle_out);
+int   ellcuda_exchange_attach(ell_handle h, int32_t nranks, int32_t rank, const void* handles /* nranks x 64 B */);
+int   ellcuda_exchange_attach_ptrs(ell_handle h, int32_t nranks, int32_t rank, void* const* blocks);
+void* ellcuda_exchange_block_ptr(ell_handle h);
 int32_t* ellcuda_status_ptr(ell_handle h);   /* device, CutStatus of the last finish       */
 int ellcuda_last_status(ell_handle h, int32_t* out_status); /* synchronises, reads status   */
 int ellcuda_set_stream(ell_handle h, void* stream);

@@ -153,6 +153,40 @@ def test_bad_arguments():
 
 
 # ---------------------------------------------------------------- sharded slabs on one GPU (ranks emulated in-process)
+@pytest.mark.parametrize("n,parts,mode", [(96, 2, 0), (130, 3, 0), (257, 4, 2), (1024, 8, 0)])
+def test_row_sharded_slabs_peer_exchange(ref, n, parts, mode):
+    """the NVLink peer-exchange path (ellcuda_exchange_attach_ptrs) with the ranks emulated on one GPU: all handles on
+    ONE stream, begin for every rank before any finish, so no kernel ever waits for a later launch"""
+    import torch
+    kw = _start(n, "matrix", 31)
+    s = ref.Space(A.KIND_ELL, n, kappa=kw["kappa"], mq=kw["mq"], xc=kw["xc"])
+    bounds = [n * p // parts for p in range(parts + 1)]
+    stream = torch.cuda.Stream()
+    shards = [Ell(kw["kappa"], kw["xc"], mq=kw["mq"], rows=(bounds[p], bounds[p + 1]), reduce_mode=mode, stream=stream.cuda_stream)
+              for p in range(parts)]
+    blocks = [sh.exchange_block_ptr() for sh in shards]
+    for p, sh in enumerate(shards):
+        sh.exchange_attach_ptrs(blocks, p)
+    with torch.cuda.stream(stream):
+        for which, g, cut in _cuts(n, 8, 15):
+            gd = torch.from_numpy(g).cuda()
+            for sh in shards:
+                sh.update_begin(which, gd.data_ptr(), cut)
+            for sh in shards:
+                sh.update_finish()
+            st_r = _ref_update(s, which, g, cut)
+            r = s.state()
+            for sh in shards:
+                assert int(sh.last_status()) == st_r
+                if mode == 0:
+                    assert sh.tsq() == r["tsq"] and sh.kappa == r["kappa"] and np.array_equal(sh.xc(), r["xc"])
+                else:
+                    assert rel_err(sh.tsq(), r["tsq"]).max() <= REL_TOL and rel_err(sh.xc(), r["xc"]).max() <= REL_TOL
+    full = np.concatenate([sh.mq for sh in shards], axis=0)
+    r = s.state()
+    assert np.array_equal(full, r["mq"]) if mode == 0 else np.abs(full - r["mq"]).max() <= REL_TOL * np.abs(r["mq"]).max()
+
+
 @pytest.mark.parametrize("n,parts,mode", [(96, 2, 0), (130, 3, 0), (257, 4, 2)])
 def test_row_sharded_slabs(ref, n, parts, mode):
     import torch

@@ -14,13 +14,13 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
-for n, mode in ((1024, 0), (1000, 0), (2048, 4)):
+for n, mode, xch in ((1024, 0, 'p2p'), (1000, 0, 'nccl'), (2048, 4, 'p2p'), (4096, 0, 'p2p')):
     rng = np.random.default_rng(3)
     a = rng.uniform(-1, 1, (n, n)) / n
     mq = np.eye(n) + a + a.T
     xc = rng.uniform(-1, 1, n)
     s = R.Space(A.KIND_ELL, n, kappa=1.0, mq=mq, xc=xc)
-    e = ShardedEll(1.0, xc, mq=mq, reduce_mode=mode, device=local)
+    e = ShardedEll(1.0, xc, mq=mq, reduce_mode=mode, device=local, exchange=xch)
     for k in range(6):
         g = W.large_n_grad(n, k)
         beta = ParallelCut(0.01, 0.10) if k != 3 else ParallelCut(5.0, 4.0)   # k=3: NoSoln, state must not move
@@ -35,7 +35,7 @@ for n, mode in ((1024, 0), (1000, 0), (2048, 4)):
     slab = e.ell.mq
     r = s.state()
     ok &= bool(np.array_equal(slab, r["mq"][e.lo:e.hi]) if mode == 0 else np.abs(slab - r["mq"][e.lo:e.hi]).max() <= 1e-9)
-    print(f"rank {rank}: n={n} mode={mode} rows [{e.lo},{e.hi}) ok={ok}", flush=True)
+    print(f"rank {rank}: n={n} mode={mode} exchange={xch} rows [{e.lo},{e.hi}) ok={ok}", flush=True)
 prob = W.bowl(1001, n=32, max_iters=300)
 prob.device = local
 out = solve_batch_sharded(prob, batch.solve_batch, rank, world)
