@@ -45,6 +45,8 @@ struct Scal {  // device-resident scalars of the Ell (src/ell.rs:9-16) + the def
     double scale;   // kappa to fold into M with the pending rank-1 (no_defer_trick), else 1
     int pending;    // 1: (ratio, scale, gt) describe a rank-1 not yet applied to M
     int status;     // CutStatus of the last finish
+    unsigned long long epoch;   // peer exchange: number of the update in flight (device-resident so that a captured
+                                // CUDA graph of one update can be replayed); bumped at the end of finish
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -94,10 +96,12 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ------------------------------------------------------------------------------------------------ kernels
 // pack[i] = {g[i], gt[i], ratio·gt[i], 0} for i < n, zeros up to npad; also keeps a copy of g for `finish`.
-__global__ void pack_kernel(const double* __restrict__ g_in, double* __restrict__ g_keep, const double* __restrict__ gt,
-                            const Scal* __restrict__ sc, double4* __restrict__ pack, long long n, long long npad) {
+__global__ void pack_kernel(const double* __restrict__ g_in, double* __restrict__ g_keep, const double* __restrict__ gt_block,
+                            int attached, const Scal* __restrict__ sc, double4* __restrict__ pack, long long n, long long npad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
+    // grad_t of the previous update: with peers attached it sits in the buffer of the other parity
+    const double* gt = attached ? gt_block + ((sc->epoch & 1ULL) ^ 1ULL) * n : gt_block;
     double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
     if (i < n) {
         const double g = g_in ? g_in[i] : 0.0;
@@ -272,24 +276,27 @@ __global__ void combine_kernel(const double* __restrict__ partial, long long ld_
 // data a slower rank still reads (see the ordering argument in DESIGN.md §5).
 constexpr int kMaxRanks = 16;
 struct PeerTable {
-    double* gt[kMaxRanks];                  // peer r's grad_t buffer for the current parity
-    unsigned long long* flag[kMaxRanks];    // peer r's flag word for THIS rank as source
+    double* blk[kMaxRanks];   // rank r's exchange block: grad_t[2][n], then kMaxRanks flag words (index = source rank)
     int nranks;
+    int rank;
 };
 
 __global__ void __launch_bounds__(1024) combine_push_kernel(const double* __restrict__ partial, long long ld_part, int nseg,
-                                                            long long w, long long c_glob0, PeerTable pt,
-                                                            unsigned long long epoch) {
+                                                            long long n, long long w, long long c_glob0, PeerTable pt,
+                                                            const Scal* __restrict__ sc) {
+    const unsigned long long epoch = sc->epoch;
+    const long long off = (long long)(epoch & 1ULL) * n + c_glob0;
     for (long long c = threadIdx.x; c < w; c += blockDim.x) {
         double acc = partial[c];
         for (int s = 1; s < nseg; ++s) acc += partial[(long long)s * ld_part + c];
-        for (int r = 0; r < pt.nranks; ++r) pt.gt[r][c_glob0 + c] = acc;
+        for (int r = 0; r < pt.nranks; ++r) pt.blk[r][off + c] = acc;
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < pt.nranks) {
         __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pt.flag[threadIdx.x]), "l"(epoch) : "memory");
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(pt.blk[threadIdx.x] + 2 * n) + pt.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
     }
 }
 
@@ -308,24 +315,26 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsign
 // omega, tsq, EllCalc, xc, kappa — one CTA, identical on every rank (src/ell.rs:103-115, 130-135).
 constexpr int kFinThreads = 1024;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)
-__global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, const double* gt,
+__global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, const double* gt_block,
                                                              double* __restrict__ xc, Scal* __restrict__ sc, long long n,
                                                              CalcConsts cc, int which, Cut cut, int no_defer, int reduce_mode,
-                                                             const unsigned long long* wait_flags, int wait_n,
-                                                             unsigned long long epoch) {
+                                                             int wait_n) {
     __shared__ double prod[kFinChunk];
     __shared__ double s_omega;
     __shared__ double s_roo;
     __shared__ int s_status;
     __shared__ int s_timeout;
     const int tid = threadIdx.x;
+    const unsigned long long epoch = sc->epoch;
+    const double* gt = wait_n > 0 ? gt_block + (epoch & 1ULL) * n : gt_block;
     if (wait_n > 0) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
+        const unsigned long long* wait_flags = reinterpret_cast<const unsigned long long*>(gt_block + 2 * n);
         if (tid == 0) s_timeout = 0;
         __syncthreads();
         if (tid < wait_n && !wait_flag(wait_flags + tid, epoch)) s_timeout = 1;
         __syncthreads();
         if (s_timeout) {
-            if (tid == 0) { sc->status = kUnknown; sc->pending = 0; }
+            if (tid == 0) { sc->status = kUnknown; sc->pending = 0; sc->epoch = epoch + 1; }
             return;
         }
     }
@@ -395,6 +404,7 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         const double roo = s_roo;
         for (long long i = tid; i < n; i += kFinThreads) xc[i] -= roo * gt[i];
     }
+    if (tid == 0 && wait_n > 0) sc->epoch = epoch + 1;   // every thread has read `epoch` before the first barrier
 }
 
 __global__ void transpose_kernel(const double* __restrict__ in, long long ld_in, double* __restrict__ out, long long rows_in,
@@ -475,7 +485,6 @@ struct ellcuda_ctx {
     int* status_host = nullptr; // pinned, CutStatus read-back
     double* xblk = nullptr;     // exchange block: grad_t[2][n] then kMaxRanks flag words (IPC-shareable cudaMalloc)
     double* gt = nullptr;       // n, current grad_t buffer inside xblk (full length; a rank writes [c0, c0+w))
-    unsigned long long epoch = 0;            // updates begun (selects the buffer parity when peers are attached)
     int nranks = 0, rank = 0;                // > 0 once ellcuda_exchange_attach* succeeded
     double* peer_blk[ellcuda::kMaxRanks] = {};   // every rank's exchange block as mapped in this process
     bool peer_opened[ellcuda::kMaxRanks] = {};   // mapped by cudaIpcOpenMemHandle (must be closed)
@@ -570,28 +579,24 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
     const int thr = 256;
     const bool flush = g_dev == nullptr;
     const bool peers = h->nranks > 0 && !flush;
-    // with peers attached grad_t alternates between the block's two buffers: `h->gt` still names the previous update's
-    const double* gt_prev = h->gt;
-    if (peers) {
-        h->epoch += 1;
-        h->gt = h->xblk + (h->epoch & 1) * h->n;
-    }
-    pack_kernel<<<(unsigned)((h->npad + thr - 1) / thr), thr, 0, s>>>(g_dev, h->g, gt_prev, h->sc, h->pack, h->n, h->npad);
+    // with peers attached grad_t alternates between the block's two buffers (parity of the device-side epoch)
+    pack_kernel<<<(unsigned)((h->npad + thr - 1) / thr), thr, 0, s>>>(g_dev, h->g, h->xblk, h->nranks > 0 ? 1 : 0, h->sc, h->pack,
+                                                                      h->n, h->npad);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cap);
-    const bool rec = h->timing && cap == cudaStreamCaptureStatusNone;
-    if (rec) ELL_CUDA_TRY(cudaEventRecord(h->ev0, s));
+    const bool rec = h->timing;
+    // inside a stream capture the records become external event-record nodes, so a replayed graph still times its sweeps
+    const unsigned evflag = cap == cudaStreamCaptureStatusNone ? cudaEventRecordDefault : cudaEventRecordExternal;
+    if (rec) ELL_CUDA_TRY(cudaEventRecordWithFlags(h->ev0, s, evflag));
     dim3 grid((unsigned)(h->ld_part / kCols), (unsigned)h->nseg);
     if ((rc_launch = launch_sweep(h, grid, s))) return rc_launch;
-    if (rec) { ELL_CUDA_TRY(cudaEventRecord(h->ev1, s)); h->timed = true; }
+    if (rec) { ELL_CUDA_TRY(cudaEventRecordWithFlags(h->ev1, s, evflag)); h->timed = true; }
     if (peers) {
         PeerTable pt;
         pt.nranks = h->nranks;
-        for (int r = 0; r < h->nranks; ++r) {
-            pt.gt[r] = h->peer_blk[r] + (h->epoch & 1) * h->n;
-            pt.flag[r] = xblk_flags(h->peer_blk[r], h->n) + h->rank;
-        }
-        combine_push_kernel<<<1, 1024, 0, s>>>(h->partial, h->ld_part, h->nseg, h->w, h->c0, pt, h->epoch);
+        pt.rank = h->rank;
+        for (int r = 0; r < h->nranks; ++r) pt.blk[r] = h->peer_blk[r];
+        combine_push_kernel<<<1, 1024, 0, s>>>(h->partial, h->ld_part, h->nseg, h->n, h->w, h->c0, pt, h->sc);
     } else if (!flush) {
         combine_kernel<<<(unsigned)((h->w + thr - 1) / thr), thr, 0, s>>>(h->partial, h->ld_part, h->nseg, h->gt, h->w, h->c0);
     }
@@ -680,7 +685,7 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->xc, d->xc, (size_t)n * 8, cudaMemcpyHostToDevice, s);
     Scal sc0;
     memset(&sc0, 0, sizeof sc0);
-    sc0.kappa = d->kappa; sc0.scale = 1.0;
+    sc0.kappa = d->kappa; sc0.scale = 1.0; sc0.epoch = 1;
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->sc, &sc0, sizeof sc0, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { free_ctx(h); return cuda_fail(e, "ellcuda_create upload", __FILE__, __LINE__); }
@@ -704,8 +709,14 @@ int ellcuda_clone(ell_handle h, ell_handle* out) {
     e = cudaMemcpyAsync(c->S, h->S, (size_t)n * h->ld * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->xc, h->xc, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->g, h->g, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->gt, h->gt, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);   // the clone is detached from peers
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->sc, h->sc, sizeof(Scal), cudaMemcpyDeviceToDevice, s);
+    // the clone is detached from peers: it keeps grad_t of the last completed update in buffer 0 and restarts its epoch
+    Scal sc_h;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&sc_h, h->sc, sizeof(Scal), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    const double* src_gt = h->nranks > 0 ? h->xblk + ((sc_h.epoch & 1ULL) ^ 1ULL) * n : h->xblk;
+    sc_h.epoch = 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->gt, src_gt, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->sc, &sc_h, sizeof(Scal), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { free_ctx(c); return cuda_fail(e, "ellcuda_clone copy", __FILE__, __LINE__); }
     *out = c;
@@ -789,8 +800,8 @@ int ellcuda_update_finish(ell_handle h) {
     ELL_DEVICE_SCOPE(h->device);
     const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
     const bool peers = h->nranks > 0;
-    finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->g, h->gt, h->xc, h->sc, h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode,
-                                                    peers ? xblk_flags(h->xblk, h->n) : nullptr, peers ? h->nranks : 0, h->epoch);
+    finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->g, h->xblk, h->xc, h->sc, h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode,
+                                                    peers ? h->nranks : 0);
     ELL_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     return ELLCUDA_OK;

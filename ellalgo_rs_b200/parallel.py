@@ -97,6 +97,17 @@ class ShardedEll:
         self.exchange()
         self.ell.update_finish()
 
+    def capture(self, which: int, grads, cut, stream):
+        """CUDA graph of len(grads) consecutive updates (sweep -> exchange -> finish each), replayable any number of
+        times: all per-update state, including the peer-exchange epoch, lives in device memory.  `stream` must be the
+        torch stream this object was created under."""
+        torch = self._torch
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for g in grads:
+                self.update_async(which, g, cut)
+        return graph
+
     def update(self, which: int, grad_dev, cut):
         self.update_async(which, grad_dev, cut)
         return self.ell.last_status()
