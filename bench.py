@@ -275,44 +275,48 @@ def main():
     if not args.skip_large_n:
         n = args.large_n
         mode = 0 if world == 1 else world    # k row segments keep 256 sweep warps per GPU when the slab has n/P columns
-        ell = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local, exchange=args.exchange)
-        grads = [torch.from_numpy(W.large_n_grad(n, k)).to(dev) for k in range(16)]
+        grads = [torch.from_numpy(W.large_n_grad(n, k)).to(dev) for k in range(20)]
         cut = ParallelCut(*W.LARGE_N_CUT)
-        for k in range(LARGE_WARMUP):
-            ell.update_async(A.UPDATE_BIAS, grads[k % 16], cut)
-        barrier()
-        ell.ell.set_timing(True)
-        # LARGE_UPDATES updates as CUDA-graph replays of 20 updates each (launch latency hidden, north_star); the sweep
-        # kernel's own duration comes from event-record nodes inside the graph (last sweep of every replay)
+        # kappa shrinks by ~1.5 % per update, so after ~290 of these cuts tsq falls under beta1^2 and the cut degrades to
+        # a single/failed cut (cheaper sweeps).  Every phase therefore starts from a fresh M = I and stays below 260.
+
+        def fresh():
+            e = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local, exchange=args.exchange)
+            for k in range(LARGE_WARMUP):
+                e.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
+            return e
+
+        # phase A — throughput: 200 updates as 10 replays of a 20-update CUDA graph (launch latency hidden, north_star)
+        ell = fresh()
         per_graph = 20
-        graph = ell.capture(A.UPDATE_BIAS, [grads[j % 16] for j in range(per_graph)], cut, stream) if not args.no_graph else None
-        if graph is not None:
-            graph.replay()
+        graph = None if args.no_graph else ell.capture(A.UPDATE_BIAS, grads[:per_graph], cut, stream)
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ell.ell.launches
-        sweeps = []
         a0.record(stream)
         if graph is not None:
             for _ in range(LARGE_UPDATES // per_graph):
                 graph.replay()
-                sweeps.append(None)
         else:
             for k in range(LARGE_UPDATES):
-                ell.update_async(A.UPDATE_BIAS, grads[(LARGE_WARMUP + k) % 16], cut)
-                if k % 10 == 9:
-                    sweeps.append(ell.ell.last_sweep_ms())   # event query of the most recent sweep (waits for it only)
+                ell.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
         a1.record(stream)
         barrier()
-        if graph is not None:   # per-sweep timing: a few more replays, reading the external event pair after each
-            sweeps = []
-            for _ in range(5):
-                graph.replay()
-                torch.cuda.synchronize()
-                sweeps.append(ell.ell.last_sweep_ms())
         t_large = max_over_ranks(a0.elapsed_time(a1) / 1e3)
         l_launch = (4 * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
         status = int(ell.ell.last_status())
+        exchange_kind = ell.exchange_kind
+        del graph, ell
+
+        # phase B — the sweep kernel alone: CUDA events around every sweep launch (same stream), eager, 60 updates
+        ell = fresh()
+        ell.ell.set_timing(True)
+        sweeps = []
+        for k in range(60):
+            ell.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
+            sweeps.append(ell.ell.last_sweep_ms())
+        barrier()
+        status_b = int(ell.ell.last_status())
         sweep_ms = float(np.median(sweeps))
         bytes_update = 16.0 * n * n                       # read M once + write M once
         gbs = bytes_update * LARGE_UPDATES / t_large / 1e9
@@ -321,28 +325,34 @@ def main():
             "metric": "Ell::update HBM GB/s at n=16384 (whole job, 16*n^2 algorithmic bytes per update)",
             "value": gbs, "unit": "GB/s", "updates_per_s": LARGE_UPDATES / t_large, "ms_per_update": 1e3 * t_large / LARGE_UPDATES,
             "n": n, "updates": LARGE_UPDATES, "warmup": LARGE_WARMUP, "scaling": "strong", "reduce_mode": mode,
-            "last_status": status, "gpu_launches": int(l_launch), "cuda_graph": graph is not None,
-            "collective": None if world == 1 else f"{ell.exchange_kind}: grad_t slabs (n*8 bytes total) " + ("stored into every peer's block over NVLink by the kernel that completes them; finish waits on device flags" if ell.exchange_kind == "p2p" else "NCCL all_gather_into_tensor per update"),
+            "last_status": status, "last_status_sweep_phase": status_b, "gpu_launches": int(l_launch),
+            "cuda_graph": not args.no_graph,
+            "collective": None if world == 1 else f"{exchange_kind}: grad_t slabs (n*8 bytes in total) " + (
+                "stored into every peer's block over NVLink by the kernel that completes them; finish waits on device flags"
+                if exchange_kind == "p2p" else "NCCL all_gather_into_tensor per update"),
             "roofline": {"bound": "hbm", "kernel": "sweep_kernel (fused deferred rank-1 + GEMV, TMA-staged)",
                          "achieved": slab_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": slab_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": slab_bytes / (sweep_ms * 1e-3) / 1e9 / 8000.0,
-                         "ms_per_launch": sweep_ms, "algorithmic_bytes_per_launch": slab_bytes, "traffic": None},
+                         "ms_per_launch": sweep_ms, "algorithmic_bytes_per_launch": slab_bytes, "traffic": None,
+                         "timing": "median of 60 CUDA-event pairs around the sweep launches of an eager run (phase B)"},
         }
-        # e2e: SearchSpace::update_bias_cut with a HOST gradient per call (H2D 8n bytes, D2H status) — whole matrix only
+        del ell
+        # phase C — e2e: SearchSpace::update_bias_cut with a HOST gradient per call (H2D 8n bytes, D2H status), whole matrix
         if world == 1:
-            hg = [torch.from_numpy(W.large_n_grad(n, k)).pin_memory() for k in range(8)]
+            ell = fresh()
+            hg = [torch.from_numpy(W.large_n_grad(n, k)).pin_memory() for k in range(20)]
             st = C.c_int32()
-            K2 = 50
+            K2 = 100
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for k in range(K2):
-                check(L.ellcuda_update(ell.ell._h, A.UPDATE_BIAS, hg[k % 8].data_ptr(), cut.beta0, 1, cut.beta1, C.byref(st)))
+                check(L.ellcuda_update(ell.ell._h, A.UPDATE_BIAS, hg[k % 20].data_ptr(), cut.beta0, 1, cut.beta1, C.byref(st)))
             t1 = time.perf_counter() - t0
             large["e2e"] = {"value": bytes_update * K2 / t1 / 1e9, "unit": "GB/s", "updates_per_s": K2 / t1,
-                            "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4, "updates": K2,
+                            "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4, "updates": K2, "last_status": int(st.value),
                             "timing": "host wall clock around synchronous ellcuda_update calls"}
-        del ell
+            del ell
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
