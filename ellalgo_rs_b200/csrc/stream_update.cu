@@ -6,7 +6,10 @@
 //
 //     sweep(k+1):   M <- (M - (ratio_k·g̃_k[hi])·g̃_k[lo]) [·kappa if no_defer_trick]     src/ell.rs:117-128, 132-135
 //                   g̃_{k+1}[c] = sum_i M[i][c]·g_{k+1}[i]   (i ascending)                src/arr.rs:426-442
-//     finish(k+1):  omega, tsq, EllCalc, xc, kappa                                         src/ell.rs:103-115, 130
+//     finish(k+1):  omega, tsq, EllCalc, xc, kappa, and {g̃, ratio·g̃} for the next sweep    src/ell.rs:103-115, 119, 130
+//
+// Two kernels per update.  The sweep's tail also does the ordered combine of row-segment partials and, for
+// row-sharded handles, pushes the finished block of g̃ into every peer GPU's memory over NVLink.
 //
 // M is symmetric bit for bit (the reference mirrors every write), so the column sum over i is the reference's row
 // sum over j, term for term and in the same order; with reduce_mode 0 grad_t and omega are bit-identical to Rust.
@@ -35,7 +38,7 @@ constexpr int kCols = 64;    // columns per warp (2 per lane)
 constexpr int kRowsDefault = 64;    // rows per TMA tile   (measured at n=16384: 64x3 682 us, 32x6 693, 48x4 692,
 constexpr int kStagesDefault = 3;   // smem ring depth      32x4 709, 48x3 753, 32x3 840, 16x8 831, 64x4 1219 [1 CTA/SM])
 constexpr int kRowsMax = 64;
-// per tile: kCols*ROWS*8 bytes of M and ROWS*32 bytes of pack {g[i], gt[i], ratio*gt[i], 0}
+// per tile: kCols*ROWS*8 bytes of M, ROWS*8 bytes of g and ROWS*16 bytes of {gt[i], ratio*gt[i]}
 
 struct Scal {  // device-resident scalars of the Ell (src/ell.rs:9-16) + the deferred rank-1
     double kappa;
@@ -95,50 +98,70 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ kernels
-// pack[i] = {g[i], gt[i], ratio·gt[i], 0} for i < n, zeros up to npad; also keeps a copy of g for `finish`.
-__global__ void pack_kernel(const double* __restrict__ g_in, double* __restrict__ g_keep, const double* __restrict__ gt_block,
-                            int attached, const Scal* __restrict__ sc, double4* __restrict__ pack, long long n, long long npad) {
+// Peer exchange (row-sharded handles attached with ellcuda_exchange_attach): the sweep CTA that completes a block of
+// 64 columns of grad_t stores it straight into EVERY rank's exchange block over NVLink (peer pointers); the last CTA
+// of the rank publishes the update's epoch in each peer's flag word; `finish_kernel` on every rank waits for all P
+// flags.  No collective call, no host involvement.  An exchange block holds two grad_t buffers (epoch parity) so
+// that a rank one update ahead never overwrites data a slower rank still reads.
+constexpr int kMaxRanks = 16;
+struct PeerTable {
+    double* blk[kMaxRanks];   // rank r's exchange block (layout: xblk_* helpers below)
+    int nranks;               // 0: no peer exchange (grad_t goes to this rank's buffer 0 only)
+    int rank;
+};
+// exchange block, in doubles: grad_t[2][n] | flags[kMaxRanks] (u64, index = source rank) | omega_part[2][kMaxRanks]
+__host__ __device__ inline size_t xblk_doubles(long long n) { return (size_t)2 * n + kMaxRanks + 2 * kMaxRanks; }
+__host__ __device__ inline unsigned long long* xblk_flags(double* blk, long long n) {
+    return reinterpret_cast<unsigned long long*>(blk + 2 * n);
+}
+__host__ __device__ inline double* xblk_omega(double* blk, long long n, int parity) { return blk + 2 * n + kMaxRanks + parity * kMaxRanks; }
+
+struct SweepArgs {
+    const double* g;           // gradient of this update, readable for npad rows (user buffer if n % 64 == 0, else a padded copy)
+    const double2* pend;       // {grad_t[i], ratio·grad_t[i]} of the deferred rank-1 (written by finish), padded with zeros
+    const Scal* sc;
+    double* partial;           // nseg × ld_part column sums per row segment
+    double* block_omega;       // per column block: sum of g[c]·grad_t[c] over its 64 columns
+    unsigned* cnt_block;       // arrivals per column block (self-resetting)
+    unsigned* cnt_all;         // column blocks completed (self-resetting)
+    double* own_blk;           // this rank's exchange block
+    long long ld_part, n, w, c_glob0;
+    int nseg;
+    int exchange;              // 0: flush only (no grad_t is produced); 1: produce grad_t (+ push to peers if attached)
+    int omega_parts;           // 1: also publish this rank's part of omega (attached, reduce_mode > 0)
+    PeerTable pt;
+};
+
+// a padded copy of the gradient, only needed when n is not a multiple of the tile height (bulk loads must stay in bounds)
+__global__ void copy_pad_kernel(const double* __restrict__ g_in, double* __restrict__ g_out, long long n, long long npad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npad) return;
-    // grad_t of the previous update: with peers attached it sits in the buffer of the other parity
-    const double* gt = attached ? gt_block + ((sc->epoch & 1ULL) ^ 1ULL) * n : gt_block;
-    double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (i < n) {
-        const double g = g_in ? g_in[i] : 0.0;
-        g_keep[i] = g;
-        v.x = g;
-        if (sc->pending) {
-            const double t = gt[i];
-            v.y = t;
-            v.z = sc->ratio * t;  // r_qg = ratio * grad_t[i]   (src/ell.rs:119)
-        }
-    }
-    pack[i] = v;
+    if (i < npad) g_out[i] = i < n ? g_in[i] : 0.0;
 }
 
 // MODE 0: every row of the tile is above the block's columns (i < c):   update = (ratio·gt[c]) · gt[i]
 // MODE 1: every row is at or below them (i >= c):                        update = (ratio·gt[i]) · gt[c]
 // MODE 2: the tile crosses the diagonal: choose per element.             (src/ell.rs:118-127: hi = max, lo = min)
 template <int MODE, bool PENDING, bool SCALE>
-__device__ __forceinline__ void tile_rows(double2* __restrict__ tile, const double4* __restrict__ pk, int lane, int nrows, int row0,
-                                          int col0, double gt_c0, double gt_c1, double rg_c0, double rg_c1, double scale, double& acc0,
-                                          double& acc1) {
+__device__ __forceinline__ void tile_rows(double2* __restrict__ tile, const double* __restrict__ gs, const double2* __restrict__ pd,
+                                          int lane, int nrows, int row0, int col0, double gt_c0, double gt_c1, double rg_c0,
+                                          double rg_c1, double scale, double& acc0, double& acc1) {
 #pragma unroll 8
-    for (int r = 0; r < nrows; ++r) {  // nrows < kRows only in the last tile of a segment (rows past n are not M)
+    for (int r = 0; r < nrows; ++r) {  // nrows < tile height only in the last tile of a segment (rows past n are not M)
         double2 m = tile[r * (kCols / 2) + lane];
-        const double4 p = pk[r];  // broadcast
+        const double gi = gs[r];       // broadcast
         if (PENDING) {
+            const double2 p = pd[r];   // broadcast: {gt[i], ratio*gt[i]}
             double u0, u1;
             if (MODE == 0) {
-                u0 = rg_c0 * p.y;
-                u1 = rg_c1 * p.y;
+                u0 = rg_c0 * p.x;
+                u1 = rg_c1 * p.x;
             } else if (MODE == 1) {
-                u0 = p.z * gt_c0;
-                u1 = p.z * gt_c1;
+                u0 = p.y * gt_c0;
+                u1 = p.y * gt_c1;
             } else {
                 const int i = row0 + r;
-                u0 = (i >= col0) ? p.z * gt_c0 : rg_c0 * p.y;
-                u1 = (i >= col0 + 1) ? p.z * gt_c1 : rg_c1 * p.y;
+                u0 = (i >= col0) ? p.y * gt_c0 : rg_c0 * p.x;
+                u1 = (i >= col0 + 1) ? p.y * gt_c1 : rg_c1 * p.x;
             }
             m.x -= u0;
             m.y -= u1;
@@ -148,24 +171,24 @@ __device__ __forceinline__ void tile_rows(double2* __restrict__ tile, const doub
             }
             tile[r * (kCols / 2) + lane] = m;
         }
-        acc0 += m.x * p.x;  // grad_t[c] += M[i][c] * g[i], i ascending
-        acc1 += m.y * p.x;
+        acc0 += m.x * gi;  // grad_t[c] += M[i][c] * g[i], i ascending
+        acc1 += m.y * gi;
     }
 }
 
 template <int kRows, int kStages, bool PENDING, bool SCALE>
-__device__ __forceinline__ void sweep_body(const CUtensorMap* map, const double4* __restrict__ pack, double* __restrict__ out,
-                                           long long w, long long row_lo, long long row_hi, long long c_glob0, double scale,
-                                           unsigned char* smem_raw) {
+__device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepArgs& a, long long row_lo, long long row_hi, double scale,
+                                           unsigned char* smem_raw, double& acc0, double& acc1) {
     constexpr int kTileBytes = kCols * kRows * 8;
-    constexpr int kPackBytes = kRows * 32;
-    // smem: [kStages tiles][kStages packs][kStages mbarriers]
-    double2* tiles = reinterpret_cast<double2*>(smem_raw);
-    double4* packs = reinterpret_cast<double4*>(smem_raw + kStages * kTileBytes);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kStages * (kTileBytes + kPackBytes));
+    constexpr int kPendBytes = kRows * 16;
+    constexpr int kGBytes = kRows * 8;
+    // smem: [kStages tiles][kStages pend rows][kStages g rows][kStages mbarriers]
+    unsigned char* tiles = smem_raw;
+    unsigned char* pends = smem_raw + kStages * kTileBytes;
+    unsigned char* gss = pends + kStages * kPendBytes;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(gss + kStages * kGBytes);
     const int lane = threadIdx.x;
-    const int cb = blockIdx.x;                 // column block of this warp
-    const long long c_loc0 = (long long)cb * kCols;  // first local column
+    const long long c_loc0 = (long long)blockIdx.x * kCols;  // first local column of this warp's block
     const int ntiles = (int)((row_hi - row_lo + kRows - 1) / kRows);
 
     if (lane == 0) {
@@ -177,42 +200,41 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const double4
     auto issue = [&](int t) {  // lane 0 only
         const int s = t % kStages;
         const long long r0 = row_lo + (long long)t * kRows;
-        mbar_expect_tx(&bars[s], kTileBytes + kPackBytes);
-        tma_load_2d(reinterpret_cast<unsigned char*>(tiles) + s * kTileBytes, map, (int)c_loc0, (int)r0, &bars[s]);
-        bulk_load_1d(reinterpret_cast<unsigned char*>(packs) + s * kPackBytes, pack + r0, kPackBytes, &bars[s]);
+        mbar_expect_tx(&bars[s], kTileBytes + kGBytes + (PENDING ? kPendBytes : 0));
+        tma_load_2d(tiles + s * kTileBytes, map, (int)c_loc0, (int)r0, &bars[s]);
+        bulk_load_1d(gss + s * kGBytes, a.g + r0, kGBytes, &bars[s]);
+        if (PENDING) bulk_load_1d(pends + s * kPendBytes, a.pend + r0, kPendBytes, &bars[s]);
     };
     if (lane == 0) {
         const int pre = ntiles < (kStages - 1) ? ntiles : (kStages - 1);
         for (int t = 0; t < pre; ++t) issue(t);
     }
 
-    // this lane's two columns (global indices) and their pending-vector entries
-    const long long cg0 = c_glob0 + c_loc0 + 2 * lane;
+    // this lane's two columns (global indices) and their entries of the deferred rank-1 vectors
+    const long long cg0 = a.c_glob0 + c_loc0 + 2 * lane;
     double gt_c0 = 0.0, gt_c1 = 0.0, rg_c0 = 0.0, rg_c1 = 0.0;
     if (PENDING) {
-        // pack is indexed by global row = global column index of the symmetric matrix
-        const double4 a = pack[cg0];
-        const double4 b = pack[cg0 + 1];  // pack is padded, always readable
-        gt_c0 = a.y; rg_c0 = a.z;
-        gt_c1 = b.y; rg_c1 = b.z;
+        const double2 p0 = a.pend[cg0], p1 = a.pend[cg0 + 1];  // pend is padded, always readable
+        gt_c0 = p0.x; rg_c0 = p0.y;
+        gt_c1 = p1.x; rg_c1 = p1.y;
     }
-    double acc0 = 0.0, acc1 = 0.0;
-    const long long blk_lo = c_glob0 + c_loc0, blk_hi = blk_lo + kCols;  // global column range of the block
+    const long long blk_lo = a.c_glob0 + c_loc0, blk_hi = blk_lo + kCols;  // global column range of the block
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % kStages;
         mbar_wait(&bars[s], (unsigned)((t / kStages) & 1));
-        double2* tile = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(tiles) + s * kTileBytes);
-        const double4* pk = reinterpret_cast<const double4*>(reinterpret_cast<unsigned char*>(packs) + s * kPackBytes);
+        double2* tile = reinterpret_cast<double2*>(tiles + s * kTileBytes);
+        const double2* pd = reinterpret_cast<const double2*>(pends + s * kPendBytes);
+        const double* gs = reinterpret_cast<const double*>(gss + s * kGBytes);
         const long long r0 = row_lo + (long long)t * kRows;
         const int nrows = (int)((row_hi - r0) < kRows ? (row_hi - r0) : kRows);
         if (r0 + kRows <= blk_lo)
-            tile_rows<0, PENDING, SCALE>(tile, pk, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
+            tile_rows<0, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
         else if (r0 >= blk_hi - 1)
-            tile_rows<1, PENDING, SCALE>(tile, pk, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
+            tile_rows<1, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
         else
-            tile_rows<2, PENDING, SCALE>(tile, pk, lane, nrows, (int)(r0 - blk_lo), 2 * lane, gt_c0, gt_c1, rg_c0, rg_c1, scale,
-                                         acc0, acc1);
+            tile_rows<2, PENDING, SCALE>(tile, gs, pd, lane, nrows, (int)(r0 - blk_lo), 2 * lane, gt_c0, gt_c1, rg_c0, rg_c1,
+                                         scale, acc0, acc1);
         if (PENDING) fence_async_smem();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0) {
@@ -229,74 +251,86 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const double4
         __syncwarp();
     }
     if (PENDING && lane == 0) bulk_wait_all();
-    const long long cl = c_loc0 + 2 * lane;
-    if (cl < w) out[cl] = acc0;
-    if (cl + 1 < w) out[cl + 1] = acc1;
 }
 
 // grid = (column blocks, row segments); block = 32 threads.
 template <int kRows, int kStages>
-__global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUtensorMap map, const double4* __restrict__ pack,
-                                                   const Scal* __restrict__ sc, double* __restrict__ partial, long long ld_part,
-                                                   long long n, long long w, long long c_glob0, int nseg) {
+__global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUtensorMap map, const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int seg = blockIdx.y;
-    const long long rows_per = ((n + nseg - 1) / nseg + kRows - 1) / kRows * kRows;
+    const int lane = threadIdx.x;
+    const int cb = blockIdx.x, seg = blockIdx.y;
+    const long long rows_per = ((a.n + a.nseg - 1) / a.nseg + kRows - 1) / kRows * kRows;
     const long long row_lo = (long long)seg * rows_per;
     long long row_hi = row_lo + rows_per;
-    if (row_hi > n) row_hi = n;
-    double* out = partial + (long long)seg * ld_part;
-    if (row_lo >= row_hi) {  // empty segment: contributes exact zeros
-        const long long cl = (long long)blockIdx.x * kCols + 2 * threadIdx.x;
-        if (cl < w) out[cl] = 0.0;
-        if (cl + 1 < w) out[cl + 1] = 0.0;
+    if (row_hi > a.n) row_hi = a.n;
+    double acc0 = 0.0, acc1 = 0.0;   // an empty segment contributes exact zeros
+    if (row_lo < row_hi) {
+        const int pending = a.sc->pending;
+        const double scale = a.sc->scale;
+        if (!pending) sweep_body<kRows, kStages, false, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
+        else if (scale == 1.0) sweep_body<kRows, kStages, true, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
+        else sweep_body<kRows, kStages, true, true>(&map, a, row_lo, row_hi, scale, smem_raw, acc0, acc1);
+    }
+    if (!a.exchange) return;   // flush: only the deferred rank-1 was wanted
+
+    // ---- tail: the last row segment of a column block sums the segments in order and publishes the block
+    const long long cl = (long long)cb * kCols + 2 * lane;   // local column of this lane
+    if (a.nseg > 1) {
+        double* out = a.partial + (long long)seg * a.ld_part;
+        out[cl] = acc0;          // ld_part is a multiple of 64: always in range
+        out[cl + 1] = acc1;
+        __threadfence();
+        unsigned prev = 0;
+        if (lane == 0) prev = atomicAdd(&a.cnt_block[cb], 1u);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev != (unsigned)(a.nseg - 1)) return;
+        if (lane == 0) a.cnt_block[cb] = 0;
+        __threadfence();
+        acc0 = __ldcg(a.partial + cl);
+        acc1 = __ldcg(a.partial + cl + 1);
+        for (int s = 1; s < a.nseg; ++s) {   // segment order: deterministic
+            acc0 += __ldcg(a.partial + (long long)s * a.ld_part + cl);
+            acc1 += __ldcg(a.partial + (long long)s * a.ld_part + cl + 1);
+        }
+    }
+    const unsigned long long epoch = a.sc->epoch;
+    const int attached = a.pt.nranks > 0;
+    const long long off = (attached ? (long long)(epoch & 1ULL) * a.n : 0) + a.c_glob0 + cl;
+    const bool v0 = cl < a.w, v1 = cl + 1 < a.w;
+    if (!attached) {
+        if (v0) a.own_blk[off] = acc0;
+        if (v1) a.own_blk[off + 1] = acc1;
         return;
     }
-    const int pending = sc->pending;
-    const double scale = sc->scale;
-    if (!pending) sweep_body<kRows, kStages, false, false>(&map, pack, out, w, row_lo, row_hi, c_glob0, 1.0, smem_raw);
-    else if (scale == 1.0) sweep_body<kRows, kStages, true, false>(&map, pack, out, w, row_lo, row_hi, c_glob0, 1.0, smem_raw);
-    else sweep_body<kRows, kStages, true, true>(&map, pack, out, w, row_lo, row_hi, c_glob0, scale, smem_raw);
-}
-
-// grad_t[c_glob0 + c] = sum over row segments, in segment order (one segment: a copy).
-__global__ void combine_kernel(const double* __restrict__ partial, long long ld_part, int nseg, double* __restrict__ gt,
-                               long long w, long long c_glob0) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= w) return;
-    double acc = partial[c];
-    for (int s = 1; s < nseg; ++s) acc += partial[(long long)s * ld_part + c];
-    gt[c_glob0 + c] = acc;
-}
-
-// Peer exchange (row-sharded handles attached with ellcuda_exchange_attach): the kernel that completes this rank's
-// slab of grad_t stores it straight into EVERY rank's exchange block over NVLink (peer pointers), then publishes the
-// update's epoch in each peer's flag word; `finish_kernel` on every rank waits for all P flags.  No NCCL call, no host
-// involvement.  The block holds two grad_t buffers (epoch parity) so that a rank one update ahead never overwrites
-// data a slower rank still reads (see the ordering argument in DESIGN.md §5).
-constexpr int kMaxRanks = 16;
-struct PeerTable {
-    double* blk[kMaxRanks];   // rank r's exchange block: grad_t[2][n], then kMaxRanks flag words (index = source rank)
-    int nranks;
-    int rank;
-};
-
-__global__ void __launch_bounds__(1024) combine_push_kernel(const double* __restrict__ partial, long long ld_part, int nseg,
-                                                            long long n, long long w, long long c_glob0, PeerTable pt,
-                                                            const Scal* __restrict__ sc) {
-    const unsigned long long epoch = sc->epoch;
-    const long long off = (long long)(epoch & 1ULL) * n + c_glob0;
-    for (long long c = threadIdx.x; c < w; c += blockDim.x) {
-        double acc = partial[c];
-        for (int s = 1; s < nseg; ++s) acc += partial[(long long)s * ld_part + c];
-        for (int r = 0; r < pt.nranks; ++r) pt.blk[r][off + c] = acc;
+    for (int r = 0; r < a.pt.nranks; ++r) {   // this block of grad_t, into every rank's buffer (NVLink stores)
+        if (v0) a.pt.blk[r][off] = acc0;
+        if (v1) a.pt.blk[r][off + 1] = acc1;
+    }
+    if (a.omega_parts) {   // this block's part of omega = sum g[c]*grad_t[c]: fixed order (lane pair, then xor tree)
+        double p = (v0 ? a.g[a.c_glob0 + cl] * acc0 : 0.0) + (v1 ? a.g[a.c_glob0 + cl + 1] * acc1 : 0.0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) a.block_omega[cb] = p;
     }
     __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < pt.nranks) {
-        __threadfence_system();
-        unsigned long long* flag = reinterpret_cast<unsigned long long*>(pt.blk[threadIdx.x] + 2 * n) + pt.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned done = atomicAdd(a.cnt_all, 1u);
+        if (done == gridDim.x - 1) {   // the whole slab of this rank is out: publish
+            *a.cnt_all = 0;
+            __threadfence();
+            const int par = (int)(epoch & 1ULL);
+            if (a.omega_parts) {
+                double om = 0.0;
+                for (unsigned b = 0; b < gridDim.x; ++b) om += __ldcg(a.block_omega + b);   // block order: deterministic
+                for (int r = 0; r < a.pt.nranks; ++r) xblk_omega(a.pt.blk[r], a.n, par)[a.pt.rank] = om;
+            }
+            __threadfence_system();
+            for (int r = 0; r < a.pt.nranks; ++r) {
+                unsigned long long* flag = xblk_flags(a.pt.blk[r], a.n) + a.pt.rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+            }
+        }
     }
 }
 
@@ -308,42 +342,53 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsign
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
         if (v >= epoch) return true;
         if (clock64() - t0 > 4000000000LL) return false;
-        __nanosleep(200);
+        __nanosleep(100);
     }
 }
 
-// omega, tsq, EllCalc, xc, kappa — one CTA, identical on every rank (src/ell.rs:103-115, 130-135).
+// omega, tsq, EllCalc, xc, kappa, and the vectors of the next deferred rank-1 — one CTA, identical on every rank
+// (src/ell.rs:103-115, 130-135).
 constexpr int kFinThreads = 1024;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)
-__global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, const double* gt_block,
-                                                             double* __restrict__ xc, Scal* __restrict__ sc, long long n,
+__global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, double* blk, double* __restrict__ xc,
+                                                             double2* __restrict__ pend, Scal* __restrict__ sc, long long n,
                                                              CalcConsts cc, int which, Cut cut, int no_defer, int reduce_mode,
-                                                             int wait_n) {
+                                                             int nranks) {
     __shared__ double prod[kFinChunk];
     __shared__ double s_omega;
     __shared__ double s_roo;
+    __shared__ double s_ratio;
     __shared__ int s_status;
     __shared__ int s_timeout;
     const int tid = threadIdx.x;
     const unsigned long long epoch = sc->epoch;
-    const double* gt = wait_n > 0 ? gt_block + (epoch & 1ULL) * n : gt_block;
-    if (wait_n > 0) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
-        const unsigned long long* wait_flags = reinterpret_cast<const unsigned long long*>(gt_block + 2 * n);
+    const int par = nranks > 0 ? (int)(epoch & 1ULL) : 0;
+    const double* gt = blk + (long long)par * n;
+    if (nranks > 0) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
+        const unsigned long long* flags = xblk_flags(blk, n);
         if (tid == 0) s_timeout = 0;
         __syncthreads();
-        if (tid < wait_n && !wait_flag(wait_flags + tid, epoch)) s_timeout = 1;
+        if (tid < nranks && !wait_flag(flags + tid, epoch)) s_timeout = 1;
         __syncthreads();
         if (s_timeout) {
             if (tid == 0) { sc->status = kUnknown; sc->pending = 0; sc->epoch = epoch + 1; }
             return;
         }
     }
-    if (reduce_mode == 0) {
+    if (nranks > 0 && reduce_mode > 0) {
+        // every rank published its part of omega with its slab: sum the parts in rank order
+        if (tid == 0) {
+            const double* parts = xblk_omega(blk, n, par);
+            double acc = 0.0;
+            for (int r = 0; r < nranks; ++r) acc += __ldcg(parts + r);
+            s_omega = acc;
+        }
+    } else if (reduce_mode == 0) {
         // grad.dot(&grad_t): products in parallel, the sum strictly left to right (src/arr.rs:443-451)
         double acc = 0.0;
         for (long long base = 0; base < n; base += kFinChunk) {
             const int len = (int)((n - base) < kFinChunk ? (n - base) : kFinChunk);
-            for (int k = tid; k < len; k += kFinThreads) prod[k] = g[base + k] * gt[base + k];
+            for (int k = tid; k < len; k += kFinThreads) prod[k] = g[base + k] * __ldcg(gt + base + k);
             __syncthreads();
             if (tid == 0) {
                 int k = 0;
@@ -358,13 +403,9 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         }
         if (tid == 0) s_omega = acc;
     } else {
-        // blocked: 1024 ordered chunks summed left to right, then a fixed binary tree — deterministic
-        const long long per = (n + kFinThreads - 1) / kFinThreads;
-        const long long lo = (long long)tid * per;
-        long long hi = lo + per;
-        if (hi > n) hi = n;
+        // blocked: thread t sums elements t, t+1024, … in order, then a fixed binary tree — deterministic
         double acc = 0.0;
-        for (long long k = lo; k < hi; ++k) acc += g[k] * gt[k];
+        for (long long k = tid; k < n; k += kFinThreads) acc += g[k] * __ldcg(gt + k);
         prod[tid] = acc;
         __syncthreads();
         for (int off = kFinThreads / 2; off > 0; off >>= 1) {
@@ -385,7 +426,9 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         s_status = status;
         if (status == kSuccess) {
             s_roo = r.rho / omega;
-            sc->ratio = r.sigma / omega;
+            const double ratio = r.sigma / omega;
+            s_ratio = ratio;
+            sc->ratio = ratio;
             double kappa = sc->kappa * r.delta;
             if (no_defer) {
                 sc->scale = kappa;
@@ -398,13 +441,17 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         } else {
             sc->pending = 0;  // state unchanged except tsq (src/ell.rs:107-109)
         }
+        if (nranks > 0) sc->epoch = epoch + 1;   // every thread has read `epoch` before the first barrier
     }
     __syncthreads();
     if (s_status == kSuccess) {
-        const double roo = s_roo;
-        for (long long i = tid; i < n; i += kFinThreads) xc[i] -= roo * gt[i];
+        const double roo = s_roo, ratio = s_ratio;
+        for (long long i = tid; i < n; i += kFinThreads) {
+            const double t = __ldcg(gt + i);
+            xc[i] -= roo * t;                            // src/ell.rs:111-115
+            pend[i] = make_double2(t, ratio * t);        // r_qg = ratio * grad_t[i]  (src/ell.rs:119), applied by the next sweep
+        }
     }
-    if (tid == 0 && wait_n > 0) sc->epoch = epoch + 1;   // every thread has read `epoch` before the first barrier
 }
 
 __global__ void transpose_kernel(const double* __restrict__ in, long long ld_in, double* __restrict__ out, long long rows_in,
@@ -463,9 +510,7 @@ int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols
     return ELLCUDA_OK;
 }
 
-inline size_t xblk_bytes(long long n) { return (size_t)2 * n * 8 + kMaxRanks * 8; }
-inline unsigned long long* xblk_flags(double* blk, long long n) { return reinterpret_cast<unsigned long long*>(blk + 2 * n); }
-constexpr size_t sweep_smem(int rows, int stages) { return (size_t)stages * (kCols * rows * 8 + rows * 32) + stages * 8 + 128; }
+constexpr size_t sweep_smem(int rows, int stages) { return (size_t)stages * (kCols * rows * 8 + rows * 24) + stages * 8 + 128; }
 
 }  // namespace
 }  // namespace ellcuda
@@ -473,24 +518,27 @@ constexpr size_t sweep_smem(int rows, int stages) { return (size_t)stages * (kCo
 // =================================================================================================== handle
 struct ellcuda_ctx {
     int device = 0;
-    long long n = 0, w = 0, c0 = 0, ld = 0, npad = 0, ld_part = 0;
+    long long n = 0, w = 0, c0 = 0, ld = 0, npad = 0, ld_part = 0, ncb = 0;
     int nseg = 1, reduce_mode = 0, no_defer = 0, use_parallel = 1;
     int tile_rows = ellcuda::kRowsDefault, stages = ellcuda::kStagesDefault;   // sweep tile shape (ELLCUDA_SWEEP=rows,stages)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     double* S = nullptr;        // n × ld, column block [c0, c0+w) of the symmetric matrix
     double* xc = nullptr;       // n
-    double* g = nullptr;        // n, gradient of the update in flight
-    double* gstage = nullptr;   // n, landing buffer for host gradients (ellcuda_update)
+    double* gpad = nullptr;     // npad: padded copy of the gradient (when n is not a multiple of the tile height), zero tail
+    double* gzero = nullptr;    // npad zeros (flush sweeps)
+    double* gstage = nullptr;   // n: landing buffer for host gradients (ellcuda_update)
+    const double* gsrc = nullptr;   // gradient of the update in flight (read again by finish)
     int* status_host = nullptr; // pinned, CutStatus read-back
-    double* xblk = nullptr;     // exchange block: grad_t[2][n] then kMaxRanks flag words (IPC-shareable cudaMalloc)
-    double* gt = nullptr;       // n, current grad_t buffer inside xblk (full length; a rank writes [c0, c0+w))
-    int nranks = 0, rank = 0;                // > 0 once ellcuda_exchange_attach* succeeded
+    double* xblk = nullptr;     // exchange block (IPC-shareable cudaMalloc): grad_t[2][n], flags, omega parts
+    double2* pend = nullptr;    // npad + kCols + 2: deferred rank-1 vectors {grad_t, ratio·grad_t}
+    double* partial = nullptr;  // nseg × ld_part
+    double* block_omega = nullptr;  // ncb
+    unsigned* counters = nullptr;   // ncb + 1
+    ellcuda::Scal* sc = nullptr;
+    int nranks = 0, rank = 0;                    // > 0 once ellcuda_exchange_attach* succeeded
     double* peer_blk[ellcuda::kMaxRanks] = {};   // every rank's exchange block as mapped in this process
     bool peer_opened[ellcuda::kMaxRanks] = {};   // mapped by cudaIpcOpenMemHandle (must be closed)
-    double4* pack = nullptr;    // npad + kCols + 2 (tail stays zero)
-    double* partial = nullptr;  // nseg × ld_part
-    ellcuda::Scal* sc = nullptr;
     CUtensorMap map;
     int which = 0;
     ellcuda::Cut cut{0.0, 0.0, false};
@@ -506,7 +554,8 @@ namespace {
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
     DevGuard guard(h->device);
-    cudaFree(h->S); cudaFree(h->xc); cudaFree(h->g); cudaFree(h->gstage); cudaFreeHost(h->status_host); cudaFree(h->pack); cudaFree(h->partial); cudaFree(h->sc);
+    cudaFree(h->S); cudaFree(h->xc); cudaFree(h->gpad); cudaFree(h->gzero); cudaFree(h->gstage); cudaFreeHost(h->status_host);
+    cudaFree(h->pend); cudaFree(h->partial); cudaFree(h->block_omega); cudaFree(h->counters); cudaFree(h->sc);
     for (int r = 0; r < kMaxRanks; ++r)
         if (h->peer_opened[r] && h->peer_blk[r]) cudaIpcCloseMemHandle(h->peer_blk[r]);
     cudaFree(h->xblk);
@@ -518,7 +567,6 @@ void free_ctx(ellcuda_ctx* h) {
 
 int alloc_ctx(ellcuda_ctx* h) {
     const long long n = h->n;
-    h->ld = (h->w + 1) & ~1LL;  // TMA needs a 16-byte row pitch
     if (const char* e = getenv("ELLCUDA_SWEEP")) {   // performance experiments: "rows,stages"
         int r = 0, st = 0;
         if (sscanf(e, "%d,%d", &r, &st) == 2 && (r == 16 || r == 32 || r == 48 || r == 64) && (st == 3 || st == 4 || st == 6 || st == 8)) {
@@ -526,82 +574,92 @@ int alloc_ctx(ellcuda_ctx* h) {
             h->stages = st;
         }
     }
+    h->ld = (h->w + 1) & ~1LL;  // TMA needs a 16-byte row pitch
     h->npad = (n + kRowsMax - 1) / kRowsMax * kRowsMax + kRowsMax;
     h->ld_part = (h->w + kCols - 1) / kCols * kCols;
+    h->ncb = h->ld_part / kCols;
+    const size_t pend_n = (size_t)(h->npad + kCols + 2);
     ELL_CUDA_TRY(cudaMalloc(&h->S, (size_t)n * h->ld * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->xc, (size_t)n * 8));
-    ELL_CUDA_TRY(cudaMalloc(&h->g, (size_t)n * 8));
-    ELL_CUDA_TRY(cudaMalloc(&h->gstage, (size_t)n * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->gpad, (size_t)h->npad * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->gzero, (size_t)h->npad * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->gstage, (size_t)h->npad * 8));
     ELL_CUDA_TRY(cudaMallocHost(&h->status_host, sizeof(int)));
-    keep_mempool(h->device);
-    ELL_CUDA_TRY(cudaMalloc(&h->xblk, xblk_bytes(n)));
-    ELL_CUDA_TRY(cudaMemset(h->xblk, 0, xblk_bytes(n)));
-    h->gt = h->xblk;
-    ELL_CUDA_TRY(cudaMalloc(&h->pack, (size_t)(h->npad + kCols + 2) * 32));
+    ELL_CUDA_TRY(cudaMalloc(&h->xblk, xblk_doubles(n) * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->pend, pend_n * 16));
     ELL_CUDA_TRY(cudaMalloc(&h->partial, (size_t)h->nseg * h->ld_part * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->block_omega, (size_t)h->ncb * 8));
+    ELL_CUDA_TRY(cudaMalloc(&h->counters, (size_t)(h->ncb + 1) * 4));
     ELL_CUDA_TRY(cudaMalloc(&h->sc, sizeof(Scal)));
     ELL_CUDA_TRY(cudaEventCreate(&h->ev0));
     ELL_CUDA_TRY(cudaEventCreate(&h->ev1));
-    ELL_CUDA_TRY(cudaMemset(h->pack, 0, (size_t)(h->npad + kCols + 2) * 32));
-    ELL_CUDA_TRY(cudaMemset(h->g, 0, (size_t)n * 8));
-    int rc = make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows);
-    if (rc) return rc;
-    return ELLCUDA_OK;
+    ELL_CUDA_TRY(cudaMemset(h->gpad, 0, (size_t)h->npad * 8));
+    ELL_CUDA_TRY(cudaMemset(h->gzero, 0, (size_t)h->npad * 8));
+    ELL_CUDA_TRY(cudaMemset(h->gstage, 0, (size_t)h->npad * 8));
+    ELL_CUDA_TRY(cudaMemset(h->xblk, 0, xblk_doubles(n) * 8));
+    ELL_CUDA_TRY(cudaMemset(h->pend, 0, pend_n * 16));
+    ELL_CUDA_TRY(cudaMemset(h->counters, 0, (size_t)(h->ncb + 1) * 4));
+    keep_mempool(h->device);
+    return make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows);
 }
 
 template <int R, int ST>
-int launch_sweep_t(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {
+int launch_sweep_t(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {
     static bool attr_set = false;   // per instantiation
     constexpr size_t smem = sweep_smem(R, ST);
     if (!attr_set) {
         ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    sweep_kernel<R, ST><<<grid, 32, smem, s>>>(h->map, h->pack, h->sc, h->partial, h->ld_part, h->n, h->w, h->c0, h->nseg);
+    sweep_kernel<R, ST><<<grid, 32, smem, s>>>(h->map, a);
     return ELLCUDA_OK;
 }
 
-int launch_sweep(ellcuda_ctx* h, dim3 grid, cudaStream_t s) {   // tile rows x ring depth (ELLCUDA_SWEEP, experiments)
+int launch_sweep(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {   // tile rows x ring depth (ELLCUDA_SWEEP, experiments)
     const int key = h->tile_rows * 100 + h->stages;
     switch (key) {
-        case 1608: return launch_sweep_t<16, 8>(h, grid, s);
-        case 3204: return launch_sweep_t<32, 4>(h, grid, s);
-        case 3206: return launch_sweep_t<32, 6>(h, grid, s);
-        case 4804: return launch_sweep_t<48, 4>(h, grid, s);
-        default: return launch_sweep_t<64, 3>(h, grid, s);
+        case 1608: return launch_sweep_t<16, 8>(h, grid, a, s);
+        case 3204: return launch_sweep_t<32, 4>(h, grid, a, s);
+        case 3206: return launch_sweep_t<32, 6>(h, grid, a, s);
+        case 4804: return launch_sweep_t<48, 4>(h, grid, a, s);
+        default: return launch_sweep_t<64, 3>(h, grid, a, s);
     }
 }
 
-// begin = pack + sweep + combine (+ push to peers).  g_dev may be null (flush: applies the pending rank-1 only).
+// begin = [padded copy of g] + sweep (deferred rank-1, column sums, ordered combine, push to peers).
+// g_dev may be null (flush: applies the pending rank-1 only, produces no grad_t).
 int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
     cudaStream_t s = h->stream;
-    int rc_launch = 0;
-    const int thr = 256;
     const bool flush = g_dev == nullptr;
-    const bool peers = h->nranks > 0 && !flush;
-    // with peers attached grad_t alternates between the block's two buffers (parity of the device-side epoch)
-    pack_kernel<<<(unsigned)((h->npad + thr - 1) / thr), thr, 0, s>>>(g_dev, h->g, h->xblk, h->nranks > 0 ? 1 : 0, h->sc, h->pack,
-                                                                      h->n, h->npad);
+    if (flush) {
+        h->gsrc = h->gzero;
+    } else if (h->n % kRowsMax == 0 && (reinterpret_cast<uintptr_t>(g_dev) & 15) == 0) {
+        h->gsrc = g_dev;      // tiles never read past n: the caller's buffer is loaded directly (no copy kernel)
+    } else {
+        const int thr = 256;
+        copy_pad_kernel<<<(unsigned)((h->npad + thr - 1) / thr), thr, 0, s>>>(g_dev, h->gpad, h->n, h->npad);
+        h->gsrc = h->gpad;
+        h->launches += 1;
+    }
+    SweepArgs a;
+    a.g = h->gsrc; a.pend = h->pend; a.sc = h->sc; a.partial = h->partial; a.block_omega = h->block_omega;
+    a.cnt_block = h->counters; a.cnt_all = h->counters + h->ncb; a.own_blk = h->xblk;
+    a.ld_part = h->ld_part; a.n = h->n; a.w = h->w; a.c_glob0 = h->c0; a.nseg = h->nseg;
+    a.exchange = flush ? 0 : 1;
+    a.omega_parts = (h->nranks > 0 && h->reduce_mode > 0) ? 1 : 0;
+    a.pt.nranks = h->nranks; a.pt.rank = h->rank;
+    for (int r = 0; r < kMaxRanks; ++r) a.pt.blk[r] = r < h->nranks ? h->peer_blk[r] : nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cap);
-    const bool rec = h->timing;
     // inside a stream capture the records become external event-record nodes, so a replayed graph still times its sweeps
     const unsigned evflag = cap == cudaStreamCaptureStatusNone ? cudaEventRecordDefault : cudaEventRecordExternal;
-    if (rec) ELL_CUDA_TRY(cudaEventRecordWithFlags(h->ev0, s, evflag));
-    dim3 grid((unsigned)(h->ld_part / kCols), (unsigned)h->nseg);
-    if ((rc_launch = launch_sweep(h, grid, s))) return rc_launch;
-    if (rec) { ELL_CUDA_TRY(cudaEventRecordWithFlags(h->ev1, s, evflag)); h->timed = true; }
-    if (peers) {
-        PeerTable pt;
-        pt.nranks = h->nranks;
-        pt.rank = h->rank;
-        for (int r = 0; r < h->nranks; ++r) pt.blk[r] = h->peer_blk[r];
-        combine_push_kernel<<<1, 1024, 0, s>>>(h->partial, h->ld_part, h->nseg, h->n, h->w, h->c0, pt, h->sc);
-    } else if (!flush) {
-        combine_kernel<<<(unsigned)((h->w + thr - 1) / thr), thr, 0, s>>>(h->partial, h->ld_part, h->nseg, h->gt, h->w, h->c0);
-    }
+    if (h->timing) ELL_CUDA_TRY(cudaEventRecordWithFlags(h->ev0, s, evflag));
+    dim3 grid((unsigned)h->ncb, (unsigned)h->nseg);
+    int rc = launch_sweep(h, grid, a, s);
+    if (rc) return rc;
+    if (h->timing) { ELL_CUDA_TRY(cudaEventRecordWithFlags(h->ev1, s, evflag)); h->timed = true; }
     ELL_CUDA_TRY(cudaGetLastError());
-    h->launches += flush ? 2 : 3;
+    h->launches += 1;
     return ELLCUDA_OK;
 }
 
@@ -622,7 +680,6 @@ int flush_pending(ellcuda_ctx* h) {  // make S hold the reference's `mq` exactly
 using namespace ellcuda;
 
 extern "C" {
-
 int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     if (!d || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
     *out = nullptr;
@@ -706,16 +763,14 @@ int ellcuda_clone(ell_handle h, ell_handle* out) {
     if (rc) { free_ctx(c); return rc; }
     cudaStream_t s = h->stream;
     const long long n = h->n;
+    // the clone is detached from peers; the deferred rank-1 travels as (pend, sc.pending/ratio/scale)
+    Scal sc_h;
     e = cudaMemcpyAsync(c->S, h->S, (size_t)n * h->ld * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->xc, h->xc, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->g, h->g, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
-    // the clone is detached from peers: it keeps grad_t of the last completed update in buffer 0 and restarts its epoch
-    Scal sc_h;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->pend, h->pend, (size_t)(h->npad + kCols + 2) * 16, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&sc_h, h->sc, sizeof(Scal), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    const double* src_gt = h->nranks > 0 ? h->xblk + ((sc_h.epoch & 1ULL) ^ 1ULL) * n : h->xblk;
     sc_h.epoch = 1;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->gt, src_gt, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->sc, &sc_h, sizeof(Scal), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { free_ctx(c); return cuda_fail(e, "ellcuda_clone copy", __FILE__, __LINE__); }
@@ -798,10 +853,10 @@ int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, do
 int ellcuda_update_finish(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
+    if (!h->gsrc) { set_error("ellcuda_update_finish without ellcuda_update_begin"); return ELLCUDA_E_ARG; }
     const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
-    const bool peers = h->nranks > 0;
-    finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->g, h->xblk, h->xc, h->sc, h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode,
-                                                    peers ? h->nranks : 0);
+    finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->gsrc, h->xblk, h->xc, h->pend, h->sc, h->n, cc, h->which, h->cut, h->no_defer,
+                                                    h->reduce_mode, h->nranks);
     ELL_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     return ELLCUDA_OK;
@@ -819,7 +874,7 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double 
     return ellcuda_last_status(h, out_status);
 }
 
-double* ellcuda_grad_t_ptr(ell_handle h) { return h ? h->gt : nullptr; }
+double* ellcuda_grad_t_ptr(ell_handle h) { return h ? h->xblk : nullptr; }
 int32_t* ellcuda_status_ptr(ell_handle h) { return h ? &h->sc->status : nullptr; }
 
 int ellcuda_last_status(ell_handle h, int32_t* out_status) {
