@@ -346,110 +346,130 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsign
     }
 }
 
-// omega, tsq, EllCalc, xc, kappa, and the vectors of the next deferred rank-1 — one CTA, identical on every rank
-// (src/ell.rs:103-115, 130-135).
+// omega, tsq, EllCalc, xc, kappa, and the vectors of the next deferred rank-1 (src/ell.rs:103-115, 119, 130-135).
+// Identical on every rank.  A few CTAs: each one derives the scalars redundantly (same inputs, same order, same bits)
+// and updates its slice of xc / pend; the CTA that arrives last — when every other CTA has read `sc` — writes the new
+// scalars back, so no CTA can observe a half-updated state.
 constexpr int kFinThreads = 1024;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)
 __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, double* blk, double* __restrict__ xc,
-                                                             double2* __restrict__ pend, Scal* __restrict__ sc, long long n,
+                                                             double2* __restrict__ pend, Scal* sc, unsigned* arrivals, long long n,
                                                              CalcConsts cc, int which, Cut cut, int no_defer, int reduce_mode,
                                                              int nranks) {
     __shared__ double prod[kFinChunk];
     __shared__ double s_omega;
-    __shared__ double s_roo;
-    __shared__ double s_ratio;
-    __shared__ int s_status;
+    __shared__ double s_kappa_in;
+    __shared__ unsigned long long s_epoch;
     __shared__ int s_timeout;
+    __shared__ Scal s_out;
+    __shared__ double s_roo;
     const int tid = threadIdx.x;
-    const unsigned long long epoch = sc->epoch;
+    if (tid == 0) {
+        s_epoch = sc->epoch;
+        s_kappa_in = sc->kappa;
+        s_timeout = 0;
+    }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
     const int par = nranks > 0 ? (int)(epoch & 1ULL) : 0;
     const double* gt = blk + (long long)par * n;
     if (nranks > 0) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
         const unsigned long long* flags = xblk_flags(blk, n);
-        if (tid == 0) s_timeout = 0;
-        __syncthreads();
         if (tid < nranks && !wait_flag(flags + tid, epoch)) s_timeout = 1;
         __syncthreads();
-        if (s_timeout) {
-            if (tid == 0) { sc->status = kUnknown; sc->pending = 0; sc->epoch = epoch + 1; }
-            return;
-        }
     }
-    if (nranks > 0 && reduce_mode > 0) {
-        // every rank published its part of omega with its slab: sum the parts in rank order
-        if (tid == 0) {
-            const double* parts = xblk_omega(blk, n, par);
-            double acc = 0.0;
-            for (int r = 0; r < nranks; ++r) acc += __ldcg(parts + r);
-            s_omega = acc;
-        }
-    } else if (reduce_mode == 0) {
-        // grad.dot(&grad_t): products in parallel, the sum strictly left to right (src/arr.rs:443-451)
-        double acc = 0.0;
-        for (long long base = 0; base < n; base += kFinChunk) {
-            const int len = (int)((n - base) < kFinChunk ? (n - base) : kFinChunk);
-            for (int k = tid; k < len; k += kFinThreads) prod[k] = g[base + k] * __ldcg(gt + base + k);
-            __syncthreads();
+    if (!s_timeout) {
+        if (nranks > 0 && reduce_mode > 0) {
+            // every rank published its part of omega with its slab: sum the parts in rank order
             if (tid == 0) {
-                int k = 0;
-                for (; k + 8 <= len; k += 8) {
-                    const double p0 = prod[k], p1 = prod[k + 1], p2 = prod[k + 2], p3 = prod[k + 3];
-                    const double p4 = prod[k + 4], p5 = prod[k + 5], p6 = prod[k + 6], p7 = prod[k + 7];
-                    acc += p0; acc += p1; acc += p2; acc += p3; acc += p4; acc += p5; acc += p6; acc += p7;
-                }
-                for (; k < len; ++k) acc += prod[k];
+                const double* parts = xblk_omega(blk, n, par);
+                double acc = 0.0;
+                for (int r = 0; r < nranks; ++r) acc += __ldcg(parts + r);
+                s_omega = acc;
             }
+        } else if (reduce_mode == 0) {
+            // grad.dot(&grad_t): products in parallel, the sum strictly left to right (src/arr.rs:443-451)
+            double acc = 0.0;
+            for (long long base = 0; base < n; base += kFinChunk) {
+                const int len = (int)((n - base) < kFinChunk ? (n - base) : kFinChunk);
+                for (int k = tid; k < len; k += kFinThreads) prod[k] = g[base + k] * __ldcg(gt + base + k);
+                __syncthreads();
+                if (tid == 0) {
+                    int k = 0;
+                    for (; k + 8 <= len; k += 8) {
+                        const double p0 = prod[k], p1 = prod[k + 1], p2 = prod[k + 2], p3 = prod[k + 3];
+                        const double p4 = prod[k + 4], p5 = prod[k + 5], p6 = prod[k + 6], p7 = prod[k + 7];
+                        acc += p0; acc += p1; acc += p2; acc += p3; acc += p4; acc += p5; acc += p6; acc += p7;
+                    }
+                    for (; k < len; ++k) acc += prod[k];
+                }
+                __syncthreads();
+            }
+            if (tid == 0) s_omega = acc;
+        } else {
+            // blocked: thread t sums elements t, t+1024, … in order, then a fixed binary tree — deterministic
+            double acc = 0.0;
+#pragma unroll 4
+            for (long long k = tid; k < n; k += kFinThreads) acc += g[k] * __ldcg(gt + k);
+            prod[tid] = acc;
             __syncthreads();
+            for (int off = kFinThreads / 2; off > 0; off >>= 1) {
+                if (tid < off) prod[tid] = prod[tid] + prod[tid + off];
+                __syncthreads();
+            }
+            if (tid == 0) s_omega = prod[0];
         }
-        if (tid == 0) s_omega = acc;
-    } else {
-        // blocked: thread t sums elements t, t+1024, … in order, then a fixed binary tree — deterministic
-        double acc = 0.0;
-        for (long long k = tid; k < n; k += kFinThreads) acc += g[k] * __ldcg(gt + k);
-        prod[tid] = acc;
-        __syncthreads();
-        for (int off = kFinThreads / 2; off > 0; off >>= 1) {
-            if (tid < off) prod[tid] = prod[tid] + prod[tid + off];
-            __syncthreads();
-        }
-        if (tid == 0) s_omega = prod[0];
     }
     __syncthreads();
     if (tid == 0) {
-        const double omega = s_omega;
-        const double tsq = sc->kappa * omega;
-        sc->tsq = tsq;
-        sc->omega = omega;
-        Rsd r;
-        const int status = ell_calc(cc, which, cut, tsq, r);
-        sc->status = status;
-        s_status = status;
-        if (status == kSuccess) {
-            s_roo = r.rho / omega;
-            const double ratio = r.sigma / omega;
-            s_ratio = ratio;
-            sc->ratio = ratio;
-            double kappa = sc->kappa * r.delta;
-            if (no_defer) {
-                sc->scale = kappa;
-                kappa = 1.0;
-            } else {
-                sc->scale = 1.0;
-            }
-            sc->kappa = kappa;
-            sc->pending = 1;
-        } else {
-            sc->pending = 0;  // state unchanged except tsq (src/ell.rs:107-109)
+        Scal o;
+        o.epoch = nranks > 0 ? epoch + 1 : epoch;
+        o.kappa = s_kappa_in;
+        o.omega = 0.0; o.tsq = 0.0; o.ratio = 0.0; o.scale = 1.0; o.pending = 0; o.status = kUnknown;
+        s_roo = 0.0;
+        if (!s_timeout) {
+            const double omega = s_omega;
+            const double tsq = s_kappa_in * omega;
+            o.tsq = tsq;
+            o.omega = omega;
+            Rsd r;
+            o.status = ell_calc(cc, which, cut, tsq, r);
+            if (o.status == kSuccess) {
+                s_roo = r.rho / omega;
+                o.ratio = r.sigma / omega;
+                double kappa = s_kappa_in * r.delta;
+                if (no_defer) {
+                    o.scale = kappa;
+                    kappa = 1.0;
+                }
+                o.kappa = kappa;
+                o.pending = 1;
+            }   // else: state unchanged except tsq (src/ell.rs:107-109)
         }
-        if (nranks > 0) sc->epoch = epoch + 1;   // every thread has read `epoch` before the first barrier
+        s_out = o;
     }
     __syncthreads();
-    if (s_status == kSuccess) {
-        const double roo = s_roo, ratio = s_ratio;
-        for (long long i = tid; i < n; i += kFinThreads) {
+    if (s_out.status == kSuccess) {
+        const double roo = s_roo, ratio = s_out.ratio;
+        const long long per = (n + gridDim.x - 1) / gridDim.x;
+        const long long lo = (long long)blockIdx.x * per;
+        const long long hi = lo + per < n ? lo + per : n;
+#pragma unroll 4
+        for (long long i = lo + tid; i < hi; i += kFinThreads) {
             const double t = __ldcg(gt + i);
             xc[i] -= roo * t;                            // src/ell.rs:111-115
             pend[i] = make_double2(t, ratio * t);        // r_qg = ratio * grad_t[i]  (src/ell.rs:119), applied by the next sweep
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(arrivals, 1u);
+        if (prev == gridDim.x - 1) {   // last CTA: everyone has read sc
+            *arrivals = 0;
+            const double old_tsq = sc->tsq;
+            *sc = s_out;
+            if (s_timeout) sc->tsq = old_tsq;
         }
     }
 }
@@ -534,7 +554,7 @@ struct ellcuda_ctx {
     double2* pend = nullptr;    // npad + kCols + 2: deferred rank-1 vectors {grad_t, ratio·grad_t}
     double* partial = nullptr;  // nseg × ld_part
     double* block_omega = nullptr;  // ncb
-    unsigned* counters = nullptr;   // ncb + 1
+    unsigned* counters = nullptr;   // ncb (per column block) + 1 (blocks done) + 1 (finish CTAs arrived)
     ellcuda::Scal* sc = nullptr;
     int nranks = 0, rank = 0;                    // > 0 once ellcuda_exchange_attach* succeeded
     double* peer_blk[ellcuda::kMaxRanks] = {};   // every rank's exchange block as mapped in this process
@@ -589,7 +609,7 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMalloc(&h->pend, pend_n * 16));
     ELL_CUDA_TRY(cudaMalloc(&h->partial, (size_t)h->nseg * h->ld_part * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->block_omega, (size_t)h->ncb * 8));
-    ELL_CUDA_TRY(cudaMalloc(&h->counters, (size_t)(h->ncb + 1) * 4));
+    ELL_CUDA_TRY(cudaMalloc(&h->counters, (size_t)(h->ncb + 2) * 4));
     ELL_CUDA_TRY(cudaMalloc(&h->sc, sizeof(Scal)));
     ELL_CUDA_TRY(cudaEventCreate(&h->ev0));
     ELL_CUDA_TRY(cudaEventCreate(&h->ev1));
@@ -598,7 +618,7 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMemset(h->gstage, 0, (size_t)h->npad * 8));
     ELL_CUDA_TRY(cudaMemset(h->xblk, 0, xblk_doubles(n) * 8));
     ELL_CUDA_TRY(cudaMemset(h->pend, 0, pend_n * 16));
-    ELL_CUDA_TRY(cudaMemset(h->counters, 0, (size_t)(h->ncb + 1) * 4));
+    ELL_CUDA_TRY(cudaMemset(h->counters, 0, (size_t)(h->ncb + 2) * 4));
     keep_mempool(h->device);
     return make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows);
 }
@@ -855,8 +875,10 @@ int ellcuda_update_finish(ell_handle h) {
     ELL_DEVICE_SCOPE(h->device);
     if (!h->gsrc) { set_error("ellcuda_update_finish without ellcuda_update_begin"); return ELLCUDA_E_ARG; }
     const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
-    finish_kernel<<<1, kFinThreads, 0, h->stream>>>(h->gsrc, h->xblk, h->xc, h->pend, h->sc, h->n, cc, h->which, h->cut, h->no_defer,
-                                                    h->reduce_mode, h->nranks);
+    long long fin_ctas = (h->n + kFinThreads - 1) / kFinThreads;
+    if (fin_ctas > 16) fin_ctas = 16;
+    finish_kernel<<<(unsigned)fin_ctas, kFinThreads, 0, h->stream>>>(h->gsrc, h->xblk, h->xc, h->pend, h->sc, h->counters + h->ncb + 1,
+                                                                     h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode, h->nranks);
     ELL_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     return ELLCUDA_OK;
