@@ -314,23 +314,29 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     }
     __threadfence_system();
     __syncwarp();
-    if (lane == 0) {
-        const unsigned done = atomicAdd(a.cnt_all, 1u);
-        if (done == gridDim.x - 1) {   // the whole slab of this rank is out: publish
-            *a.cnt_all = 0;
-            __threadfence();
-            const int par = (int)(epoch & 1ULL);
-            if (a.omega_parts) {
-                double om = 0.0;
-                for (unsigned b = 0; b < gridDim.x; ++b) om += __ldcg(a.block_omega + b);   // block order: deterministic
-                for (int r = 0; r < a.pt.nranks; ++r) xblk_omega(a.pt.blk[r], a.n, par)[a.pt.rank] = om;
-            }
-            __threadfence_system();
-            for (int r = 0; r < a.pt.nranks; ++r) {
-                unsigned long long* flag = xblk_flags(a.pt.blk[r], a.n) + a.pt.rank;
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
-            }
+    unsigned done = 0;
+    if (lane == 0) done = atomicAdd(a.cnt_all, 1u);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != gridDim.x - 1) return;
+    // the whole slab of this rank is out: publish (the warp that arrived last does it)
+    if (lane == 0) *a.cnt_all = 0;
+    __threadfence();
+    const int par = (int)(epoch & 1ULL);
+    if (a.omega_parts) {
+        double om = 0.0;   // block order, strictly sequential: deterministic.  Loads are coalesced, the adds walk the lanes.
+        for (unsigned base = 0; base < gridDim.x; base += 32) {
+            const unsigned b = base + lane;
+            const double v = b < gridDim.x ? __ldcg(a.block_omega + b) : 0.0;
+            const unsigned cnt = gridDim.x - base < 32 ? gridDim.x - base : 32;
+            for (unsigned j = 0; j < cnt; ++j) om += __shfl_sync(0xffffffffu, v, j);
         }
+        if (lane < a.pt.nranks) xblk_omega(a.pt.blk[lane], a.n, par)[a.pt.rank] = om;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < a.pt.nranks) {
+        unsigned long long* flag = xblk_flags(a.pt.blk[lane], a.n) + a.pt.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
     }
 }
 
