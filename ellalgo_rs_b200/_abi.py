@@ -16,7 +16,7 @@ EXIT_NAMES = {1: "NoSoln", 2: "NoEffect", 4: "Tol", 5: "MaxIt", 6: "Feasible"}
 
 KIND_ELL, KIND_ELLSTABLE = 0, 1
 UPDATE_BIAS, UPDATE_CENTRAL, UPDATE_Q = 0, 1, 2
-MODE_OPTIM, MODE_FEAS, MODE_OPTIM_Q = 0, 1, 2
+MODE_OPTIM, MODE_FEAS, MODE_OPTIM_Q, MODE_BSEARCH = 0, 1, 2, 3
 
 (ORACLE_EXAMPLE1, ORACLE_EXAMPLE1_RR, ORACLE_EXAMPLE4, ORACLE_QUASICVX, ORACLE_PROFIT,
  ORACLE_PROFIT_RB, ORACLE_PROFIT_Q, ORACLE_LOWPASS, ORACLE_BOWL, ORACLE_LMI, ORACLE_EXAMPLE2,

@@ -211,6 +211,7 @@ struct OrExample3 {  // src/example3.rs:10-60 (feasibility; `target` is what Ora
         idx = -1;
         target = a.params ? a.params[pid * a.params_stride] : -1e100;
     }
+    __device__ void update(double gamma) { target = gamma; }   // OracleFeas::update, src/example3.rs:56-58
     __device__ bool assess_feas(const double (&x)[2], double (&g)[2], Cut& cut) {
         for (int k = 0; k < 4; ++k) {
             idx += 1;
@@ -510,6 +511,36 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
                     if (status != kSuccess) { exit_status = status; break; }
                     if (sp.tsq < a.tolerance) { exit_status = kExitTol; break; }
                 }
+            } else if constexpr (MODE == ELL_MODE_BSEARCH) {  // bsearch :441-466 over BSearchAdaptor::assess_bs :409-418
+                const double* p = a.params + pid * a.params_stride;
+                double lower = gamma, upper = p[0];
+                const double u_orig = upper, outer_tol = p[1];
+                const long long outer_max = (long long)p[2];
+                om.target = -1e100;   // MyOracle3::default(); params[] belong to the search here, not to the oracle
+                exit_status = kExitMaxIt;
+                for (niter = 0; niter < outer_max; ++niter) {
+                    const double tau = (upper - lower) / 2.0;
+                    if (tau < outer_tol) { exit_status = kExitTol; break; }
+                    double gm = lower;
+                    gm += tau;
+                    Space trial = sp;          // let mut space = self.space.clone();
+                    om.update(gm);
+                    bool feasible = false;
+                    for (long long it = 0; it < a.max_iters; ++it) {   // cutting_plane_feas :205-227
+                        if (!om.assess_feas(trial.xc, g, cut)) { feasible = true; break; }
+                        const int status = trial.update(cc, kBias, g, cut);
+                        if (status != kSuccess || trial.tsq < a.tolerance) break;
+                    }
+                    if (feasible) {
+                        sp.xc[0] = trial.xc[0]; sp.xc[1] = trial.xc[1];   // self.space.set_xc(x)
+                        upper = gm;
+                    } else {
+                        lower = gm;
+                    }
+                }
+                has_best = upper != u_orig;
+                best[0] = sp.xc[0]; best[1] = sp.xc[1];
+                gamma = upper;
             } else {  // optim_q :331-374
                 bool retry = false;
                 for (; niter < a.max_iters; ++niter) {
@@ -589,6 +620,7 @@ int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm
     ELL_CASE(ELL_ORACLE_PROFIT_Q, OrProfitQ, ELL_MODE_OPTIM_Q)
     ELL_CASE(ELL_ORACLE_EXAMPLE2, OrExample2, ELL_MODE_FEAS)
     ELL_CASE(ELL_ORACLE_EXAMPLE3, OrExample3, ELL_MODE_FEAS)
+    ELL_CASE(ELL_ORACLE_EXAMPLE3, OrExample3, ELL_MODE_BSEARCH)
     ELL_CASE(ELL_ORACLE_HALFPLANE, OrHalfPlane, ELL_MODE_FEAS)
     ELL_CASE(ELL_ORACLE_ALWAYS_CUT, OrAlwaysCut, ELL_MODE_FEAS)
     ELL_CASE(ELL_ORACLE_ALWAYS_CUT, OrAlwaysCut, ELL_MODE_OPTIM)

@@ -96,7 +96,7 @@ int validate(const ell_batch_desc* d, const ell_batch_result* r) {
     if (d->max_iters < 0) { set_error("max_iters must be non-negative"); return ELLCUDA_E_ARG; }
     if (!d->kappa0 || !d->xc0) { set_error("kappa0 and xc0 are required"); return ELLCUDA_E_ARG; }
     if (d->kind != ELL_KIND_ELL && d->kind != ELL_KIND_ELLSTABLE) { set_error("bad kind"); return ELLCUDA_E_ARG; }
-    if (d->mode < ELL_MODE_OPTIM || d->mode > ELL_MODE_OPTIM_Q) { set_error("bad mode"); return ELLCUDA_E_ARG; }
+    if (d->mode < ELL_MODE_OPTIM || d->mode > ELL_MODE_BSEARCH) { set_error("bad mode"); return ELLCUDA_E_ARG; }
     if (d->oracle_id < 0 || d->oracle_id >= ELL_ORACLE_COUNT) { set_error("bad oracle_id"); return ELLCUDA_E_ARG; }
     if (!r->num_iters || !r->exit_status) { set_error("num_iters and exit_status outputs are required"); return ELLCUDA_E_ARG; }
     if (d->mode != ELL_MODE_FEAS && !d->gamma0) { set_error("gamma0 is required in optim modes"); return ELLCUDA_E_ARG; }

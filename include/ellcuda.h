@@ -65,6 +65,11 @@ extern "C" {
 #define ELL_MODE_OPTIM    0 /* cutting_plane_optim   src/cutting_plane.rs:286-313 */
 #define ELL_MODE_FEAS     1 /* cutting_plane_feas    src/cutting_plane.rs:205-227 */
 #define ELL_MODE_OPTIM_Q  2 /* cutting_plane_optim_q src/cutting_plane.rs:331-374 */
+#define ELL_MODE_BSEARCH  3 /* bsearch over BSearchAdaptor<Oracle, Space>  src/cutting_plane.rs:376-466:
+                               gamma0[i] = lower end, params[i] = {upper end, outer tolerance, outer max_iters};
+                               max_iters / tolerance are the adaptor's (inner) Options.  Results: num_iters = outer
+                               iterations, has_xbest = `upper != u_orig` (the bool bsearch returns), gamma = final upper,
+                               xbest = the adaptor's space.xc() (last feasible point).  Oracle: ELL_ORACLE_EXAMPLE3.   */
 
 /* ---- built-in device oracles (the reference's own oracle structs, restated on device) -- */
 #define ELL_ORACLE_EXAMPLE1     0 /* src/example1.rs:8-30            optim n=2  no params   */

@@ -10,7 +10,7 @@
 // no FMA contraction (build with -ffp-contract=off), no reassociation, sums sequential from
 // 0.0, libm = glibc (what Rust's f64::exp/ln/cos/sqrt call on Linux).
 //
-// Pinning: oracle/selftest.cpp checks this file against every iteration count and
+// Pinning: tests/test_oracle_pins.py checks this file against every iteration count and
 // known-answer vector the reference's own tests hold for the path.
 #pragma once
 #include <cmath>
@@ -401,17 +401,23 @@ struct BSearchAdaptor {
         return false;
     }
 };
+// `final_upper` (not in the reference's signature) reports the interval's upper end on return, for parity checks.
 template <class OracleBS>
-std::pair<bool, std::size_t> bsearch(OracleBS& omega, std::pair<double, double> intrvl, const Options& opt) {  // :441-466
+std::pair<bool, std::size_t> bsearch(OracleBS& omega, std::pair<double, double> intrvl, const Options& opt,
+                                     double* final_upper = nullptr) {  // :441-466
     double lower = intrvl.first, upper = intrvl.second;
     const double u_orig = upper;
     for (std::size_t niter = 0; niter < opt.max_iters; ++niter) {
         const double tau = (upper - lower) / 2.0;
-        if (tau < opt.tolerance) return {upper != u_orig, niter};
+        if (tau < opt.tolerance) {
+            if (final_upper) *final_upper = upper;
+            return {upper != u_orig, niter};
+        }
         double gamma = lower;
         gamma += tau;
         if (omega.assess_bs(gamma)) upper = gamma; else lower = gamma;
     }
+    if (final_upper) *final_upper = upper;
     return {upper != u_orig, opt.max_iters};
 }
 

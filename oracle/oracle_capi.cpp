@@ -84,7 +84,21 @@ int solve_one(const ell_batch_desc& d, const ell_batch_result& r, int64_t i) {
             break;
         }
         case ELL_ORACLE_EXAMPLE2: { Example2 o; feas(o); break; }
-        case ELL_ORACLE_EXAMPLE3: { Example3 o; if (p) o.target = p[0]; feas(o); break; }
+        case ELL_ORACLE_EXAMPLE3: {
+            if (d.mode == ELL_MODE_BSEARCH) {   // src/example3.rs:68-85 generalised: interval [gamma0, p[0]], outer Options{p[2], p[1]}
+                BSearchAdaptor<Example3, Space> ad{Example3{}, sp, opt};
+                double upper = p[0];
+                const Options outer{static_cast<std::size_t>(p[2]), p[1]};
+                auto r = bsearch(ad, {gamma, p[0]}, outer, &upper);
+                sp = ad.space;
+                rr.num_iters = r.second;
+                rr.exit_status = r.second < outer.max_iters ? ExitTol : ExitMaxIt;
+                if (r.first) rr.xbest = sp.xc;
+                gamma = upper;
+                break;
+            }
+            Example3 o; if (p) o.target = p[0]; feas(o); break;
+        }
         case ELL_ORACLE_HALFPLANE: { HalfPlane o; feas(o); break; }
         case ELL_ORACLE_ALWAYS_CUT: {
             AlwaysCut o;

@@ -112,6 +112,23 @@ def test_profit_rb_and_q(ref):  # :225-260
     assert_parity(g, r, exact=True, what="profit_q")
 
 
+def test_bsearch_on_device(ref):  # src/example3.rs:68-85: bsearch + BSearchAdaptor, whole nested loop on the device
+    prob = BatchProblem(oracle_id=A.ORACLE_EXAMPLE3, n=2, count=1, mode=A.MODE_BSEARCH, kappa0=100.0, gamma0=-100.0,
+                        params=[100.0, 1e-8, 2000.0], tolerance=1e-8)
+    g, r = both(ref, prob)
+    assert (g.has_xbest[0], g.num_iters[0]) == (1, 34)
+    assert_parity(g, r, exact=True, what="bsearch example3")
+    rng = np.random.default_rng(5)
+    cnt = 500
+    params = np.stack([rng.uniform(-50, 150, cnt), 10.0 ** rng.uniform(-9, -3, cnt), rng.integers(5, 60, cnt).astype(float)], axis=1)
+    for kind in (A.KIND_ELL, A.KIND_ELLSTABLE):
+        prob = BatchProblem(oracle_id=A.ORACLE_EXAMPLE3, n=2, count=cnt, mode=A.MODE_BSEARCH, kind=kind,
+                            kappa0=rng.uniform(1.0, 200.0, cnt), xc0=rng.uniform(-3, 3, (cnt, 2)),
+                            gamma0=rng.uniform(-150, -60, cnt), params=params, tolerance=1e-8, max_iters=300)
+        g, r = both(ref, prob)
+        assert_parity(g, r, exact=True, what=f"bsearch random kind={kind}")
+
+
 def test_flags_n2(ref):
     for kw in (dict(no_defer_trick=True), dict(use_parallel_cut=False)):
         prob = BatchProblem(oracle_id=A.ORACLE_EXAMPLE4, n=2, count=2, kappa0=10.0, gamma0=-math.inf, tolerance=1e-10, **kw)

@@ -46,6 +46,12 @@ def test_example3_bsearch(ref):  # src/example3.rs:68-85
     assert (bool(f.value), it) == (True, 34)
 
 
+def test_example3_bsearch_batched_form(ref):  # the same test through the batch descriptor's MODE_BSEARCH
+    o = one(ref, oracle_id=A.ORACLE_EXAMPLE3, n=2, mode=A.MODE_BSEARCH, kappa0=100.0, gamma0=-100.0, params=[100.0, 1e-8, 2000.0],
+            tolerance=1e-8)
+    assert (o.has_xbest[0], o.num_iters[0], o.exit_status[0]) == (1, 34, A.EXIT_TOL)
+
+
 def test_profit(ref):  # src/oracles/profit_oracle.rs:207-223
     o = ref.solve(W.profit(1))
     assert o.num_iters[0] == 83 and o.has_xbest[0] == 1 and o.xbest[0, 0] <= math.log(30.5)
