@@ -360,7 +360,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import ellref_py as R
         T = R.hardware_threads()
-        sample = max(4 * T, 32)
+        sample = max(256 * T, 512)    # ≈10 s of CPU work on 16 threads
         sp = W.lowpass(sample, table, n=N_TAPS)
         t0 = time.perf_counter()
         o = R.solve(sp, T)
