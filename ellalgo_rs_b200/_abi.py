@@ -1,7 +1,7 @@
 """ctypes mirror of include/ellcuda.h (structs and constants only, no library loading).
 
-Kept separate so that the CPU checker under oracle/ can describe its inputs with the very
-same records the product takes.
+Kept separate so that test infrastructure can describe its inputs with the very same records the
+product takes without loading the library.
 """
 import ctypes as C
 
