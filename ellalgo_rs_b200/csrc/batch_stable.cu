@@ -17,6 +17,8 @@
 //            LMI gradient sym_quad never yields -0.0; a non-finite gradient would differ in NaN placement only).
 // The strict lower triangle of the reference's matrix is scratch that no API can observe (EllStable's fields are
 // private, src/ell_stable.rs:9-15); it is recomputed on the fly instead of stored.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ellcuda {
@@ -125,11 +127,18 @@ __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, doub
     const double* f1 = L.fp + (k1 < n ? k1 : 0) * L.fstride;
     for (int i = 0; i < pos; ++i) {
         const double wi = wm.swit[i];
-        for (int j = 0; j < pos; ++j) {
+        int e = tri_index(i, 0);
+        for (int j = 0; j <= i; ++j, ++e) {          // F[i][j], j <= i: row i of the packed lower triangle
             const double wj = wm.swit[j];
-            const int e = i >= j ? tri_index(i, j) : tri_index(j, i);
             r0 += wi * f0[e] * wj;
             r1 += wi * f1[e] * wj;
+        }
+        e = tri_index(i + 1, i);
+        for (int j = i + 1; j < pos; ++j) {           // F[i][j] = F[j][i], j > i: walk down column i
+            const double wj = wm.swit[j];
+            r0 += wi * f0[e] * wj;
+            r1 += wi * f1[e] * wj;
+            e += j + 1;
         }
     }
     g0 = k0 < n ? r0 : 0.0;
@@ -232,8 +241,8 @@ __device__ int stable_update(const CalcConsts& cc, const WarpMem& wm, int lane, 
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <bool DIAG>
-__global__ void __launch_bounds__(512) batch_stable_kernel(const BatchArgs a, int warps, int fstride, int per_warp_doubles) {
+template <bool DIAG, int MAXT>
+__global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, int warps, int fstride, int per_warp_doubles) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n, m = a.aux[0], tri = m * (m + 1) / 2;
@@ -355,19 +364,28 @@ int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int s
     const size_t budget = 227 * 1024;
     if (fixed + (size_t)per_warp * 8 > budget) { set_error("F table too large for shared memory"); return ELLCUDA_E_ARG; }
     int warps = (int)((budget - fixed) / ((size_t)per_warp * 8));
-    if (warps > 16) warps = 16;
+    // measured (n=64, m=16, diagonal start, 32768 problems): 8 warps 38.9, 16 58.9, 20 63.3, 24 65.4, 28 67.0 M iter/s —
+    // the serial LDLT division chain wants every warp the register file can hold
+    int cap = 28;
+    if (const char* e = getenv("ELLCUDA_LMI_WARPS")) cap = atoi(e);   // performance experiments
+    if (cap < 1) cap = 1;
+    if (cap > 28) cap = 28;
+    if (warps > cap) warps = cap;
     const size_t smem = fixed + (size_t)warps * per_warp * 8;
     long long blocks = sm_count;
     const long long need = (a.count + warps - 1) / warps;
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    if (diag) {
-        ELL_CUDA_TRY(cudaFuncSetAttribute(batch_stable_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        batch_stable_kernel<true><<<(unsigned)blocks, warps * 32, smem, s>>>(a, warps, fstride, per_warp);
-    } else {
-        ELL_CUDA_TRY(cudaFuncSetAttribute(batch_stable_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        batch_stable_kernel<false><<<(unsigned)blocks, warps * 32, smem, s>>>(a, warps, fstride, per_warp);
-    }
+    auto launch = [&](auto kern) -> int {
+        ELL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, warps * 32, smem, s>>>(a, warps, fstride, per_warp);
+        return ELLCUDA_OK;
+    };
+    int rc;
+    if (diag) rc = warps > 20 ? launch(batch_stable_kernel<true, 896>) : warps > 16 ? launch(batch_stable_kernel<true, 640>)
+                                                                                     : launch(batch_stable_kernel<true, 512>);
+    else rc = launch(batch_stable_kernel<false, 512>);
+    if (rc) return rc;
     ELL_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return ELLCUDA_OK;
