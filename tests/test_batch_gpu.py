@@ -263,3 +263,90 @@ def test_lmi_bad_arguments():
         batch.solve_batch(prob)
     with pytest.raises(EllCudaError):
         batch.solve_batch(W.lmi(2, n=65, m=4))
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases_warp_and_lmi_kernels(ref):
+    t = batch.lowpass_table(32)
+    for prob in (W.bowl(1, n=32, max_iters=50), W.bowl(9, n=32, max_iters=0), W.lowpass(1, t, max_iters=3),
+                 W.lowpass(3, t, max_iters=0), W.lmi(1, n=64, m=16), W.lmi(5, n=64, m=16, general=True, upper_scale=1e-3)):
+        g, r = both(ref, prob)
+        assert_parity(g, r, exact=True, what=f"edge oracle={prob.oracle_id} count={prob.count} max_iters={prob.max_iters}")
+    prob = W.lmi(3, n=12, m=4)
+    prob.max_iters = 0
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what="lmi max_iters=0")
+
+
+def test_lowpass_flags_and_per_instance_kappa(ref):
+    t = batch.lowpass_table(32)
+    for kw in (dict(no_defer_trick=True), dict(use_parallel_cut=False)):
+        prob = W.lowpass(4, t, max_iters=3000)
+        for k, v in kw.items():
+            setattr(prob, k, v)
+        prob.kappa0 = np.array([40.0, 10.0, 80.0, 25.0])
+        g, r = both(ref, prob)
+        assert_parity(g, r, exact=True, what=f"lowpass {kw}")
+
+
+def test_non_finite_inputs_propagate_like_the_reference(ref):
+    """no guard is added that the reference does not have: NaN / inf centres give the same status"""
+    prob = W.bowl(4, n=32, max_iters=50)
+    prob.xc0 = np.zeros((4, 32))
+    prob.xc0[1, 3] = np.nan
+    prob.xc0[2, 0] = np.inf
+    prob.params[3, :] = 0.0          # target == centre: g = 0, omega = 0, sigma = 0/0 — Success with NaN state, then tsq<tol
+    g, r = both(ref, prob)
+    assert np.array_equal(g.num_iters, r.num_iters) and np.array_equal(g.exit_status, r.exit_status)
+    assert np.array_equal(g.has_xbest, r.has_xbest)
+    assert np.array_equal(np.isnan(g.xc), np.isnan(r.xc)) and np.array_equal(np.isnan(g.tsq), np.isnan(r.tsq))
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes, size-independent properties
+def test_full_size_profit_one_million(ref):
+    """configs[1]: 2^20 profit problems.  Properties: problem 0 is the reference test (83 iterations); a problem's
+    result does not depend on its position or on the batch around it (the first 4096 equal the checker's, a duplicated
+    block equals the original); re-running gives identical bits."""
+    cnt = 1 << 20
+    prob = W.profit(cnt)
+    prob.params[cnt // 2: cnt // 2 + 4096] = prob.params[:4096]
+    g = batch.solve_batch(prob)
+    assert g.num_iters[0] == 83 and (g.exit_status == A.EXIT_TOL).all() and g.has_xbest.all()
+    r = ref.solve(W.profit(4096))
+    for f in ("num_iters", "xbest", "gamma"):
+        assert np.array_equal(getattr(g, f)[:4096], getattr(r, f))
+        assert np.array_equal(getattr(g, f)[cnt // 2: cnt // 2 + 4096], getattr(r, f))
+    g2 = batch.solve_batch(prob)
+    assert np.array_equal(g.xbest, g2.xbest) and np.array_equal(g.num_iters, g2.num_iters)
+
+
+def test_full_size_lowpass_64k_order_independent(ref):
+    """configs[2]: 65536 lowpass n=32 problems.  The dynamic problem queue must not leak state between problems:
+    solving the batch in reversed order gives the reversed results, bit for bit; the head of the batch equals the checker."""
+    t = batch.lowpass_table(32)
+    cnt = 1 << 16
+    prob = W.lowpass(cnt, t)
+    g = batch.solve_batch(prob)
+    rev = W.lowpass(cnt, t)
+    rev.params = np.ascontiguousarray(prob.params[::-1])
+    rev.gamma0 = np.ascontiguousarray(prob.gamma0[::-1])
+    gr = batch.solve_batch(rev)
+    for f in ("num_iters", "exit_status", "has_xbest", "xbest", "gamma"):
+        assert np.array_equal(getattr(g, f), getattr(gr, f)[::-1]), f
+    r = ref.solve(W.lowpass(48, t))
+    assert np.array_equal(g.num_iters[:48], r.num_iters) and np.array_equal(g.xbest[:48], r.xbest)
+    assert g.num_iters[0] == 12481
+
+
+def test_full_size_bowl_one_million(ref):
+    """SURVEY C3': 2^20 bowl problems at n=32 (max_iters capped at 200 for wall time: every problem hits MAXIT)"""
+    cnt = 1 << 20
+    prob = W.bowl(cnt, n=32, max_iters=200)
+    g = batch.solve_batch(prob)
+    assert (g.num_iters == 200).all() and (g.exit_status == A.EXIT_MAXIT).all()
+    idx = np.r_[0:64, cnt - 64:cnt]
+    sub = W.bowl(cnt, n=32, max_iters=200)
+    sub = BatchProblem(oracle_id=A.ORACLE_BOWL, n=32, count=idx.size, kappa0=100.0, xc0=np.zeros(32), gamma0=math.inf,
+                       params=np.ascontiguousarray(prob.params[idx]), max_iters=200, tolerance=1e-10)
+    r = ref.solve(sub)
+    assert np.array_equal(g.xc[idx], r.xc) and np.array_equal(g.gamma[idx], r.gamma) and np.array_equal(g.kappa[idx], r.kappa)
