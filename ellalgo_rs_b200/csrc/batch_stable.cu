@@ -370,6 +370,7 @@ int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int s
     if (const char* e = getenv("ELLCUDA_LMI_WARPS")) cap = atoi(e);   // performance experiments
     if (cap < 1) cap = 1;
     if (cap > 28) cap = 28;
+    if (!diag && cap > 16) cap = 16;   // the GENERAL variant is compiled for at most 512 threads
     if (warps > cap) warps = cap;
     const size_t smem = fixed + (size_t)warps * per_warp * 8;
     long long blocks = sm_count;
