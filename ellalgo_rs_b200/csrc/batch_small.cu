@@ -131,6 +131,7 @@ struct EllStableReg {  // src/ell_stable.rs:9-15
 //            feas: bool assess_feas(x, g, cut) -> true if a cut was returned (false = feasible);
 //            optim_q: assess_optim_q(x, gamma, retry, g, cut, xq, more_alt) -> shrunk.
 struct OrExample1 {  // src/example1.rs:8-30
+    static constexpr int kN = 2;
     __device__ void init(const BatchArgs&, long long) {}
     __device__ bool assess_optim(const double (&x)[2], double& gamma, double (&g)[2], Cut& cut) {
         const double f0 = x[0] + x[1];
@@ -147,6 +148,7 @@ struct OrExample1 {  // src/example1.rs:8-30
 };
 
 struct OrExample1RR {  // src/example1_rr.rs:13-53
+    static constexpr int kN = 2;
     int idx;
     __device__ void init(const BatchArgs&, long long) { idx = -1; }
     __device__ bool assess_optim(const double (&x)[2], double& gamma, double (&g)[2], Cut& cut) {
@@ -178,6 +180,7 @@ __device__ inline void example4_grad(int idx, double sign3, double (&g)[2]) {
 }
 
 struct OrExample4 {  // src/example4.rs:10-57
+    static constexpr int kN = 2;
     int idx;
     __device__ void init(const BatchArgs&, long long) { idx = -1; }
     __device__ bool assess_optim(const double (&x)[2], double& gamma, double (&g)[2], Cut& cut) {
@@ -205,6 +208,7 @@ struct OrExample4 {  // src/example4.rs:10-57
 };
 
 struct OrExample3 {  // src/example3.rs:10-60 (feasibility; `target` is what OracleFeas::update sets)
+    static constexpr int kN = 2;
     int idx;
     double target;
     __device__ void init(const BatchArgs& a, long long pid) {
@@ -234,6 +238,7 @@ struct OrExample3 {  // src/example3.rs:10-60 (feasibility; `target` is what Ora
 };
 
 struct OrQuasicvx {  // src/quasicvx.rs:11-51
+    static constexpr int kN = 2;
     int idx;
     __device__ void init(const BatchArgs&, long long) { idx = -1; }
     __device__ bool assess_optim(const double (&x)[2], double& gamma, double (&g)[2], Cut& cut) {
@@ -256,6 +261,7 @@ struct OrQuasicvx {  // src/quasicvx.rs:11-51
 };
 
 struct OrProfit {  // src/oracles/profit_oracle.rs:42-114
+    static constexpr int kN = 2;
     int idx;
     double log_p_scale, log_k, v0, v1, a0, a1, log_cobb, vx, q0, q1;
     __device__ void setup(double p, double scale, double limit, double a0_, double a1_, double v0_, double v1_) {  // :54-68
@@ -313,6 +319,7 @@ struct OrProfit {  // src/oracles/profit_oracle.rs:42-114
 };
 
 struct OrProfitRb {  // src/oracles/profit_oracle.rs:116-161
+    static constexpr int kN = 2;
     OrProfit omega;
     double uie0, uie1, a0, a1;
     __device__ void init(const BatchArgs& a, long long pid) {
@@ -332,6 +339,7 @@ struct OrProfitRb {  // src/oracles/profit_oracle.rs:116-161
 };
 
 struct OrProfitQ {  // src/oracles/profit_oracle.rs:163-198
+    static constexpr int kN = 2;
     OrProfit omega;
     double yd[2];
     __device__ void init(const BatchArgs& a, long long pid) { omega.init(a, pid); yd[0] = 0.0; yd[1] = 0.0; }
@@ -362,6 +370,7 @@ struct OrProfitQ {  // src/oracles/profit_oracle.rs:163-198
 };
 
 struct OrExample2 {  // tests/example2_tests.rs:12-48
+    static constexpr int kN = 2;
     int idx;
     __device__ void init(const BatchArgs&, long long) { idx = -1; }
     __device__ bool assess_feas(const double (&x)[2], double (&g)[2], Cut& cut) {
@@ -381,6 +390,7 @@ struct OrExample2 {  // tests/example2_tests.rs:12-48
 };
 
 struct OrHalfPlane {  // tests/cutting_plane_tests.rs:12-28
+    static constexpr int kN = 2;
     __device__ void init(const BatchArgs&, long long) {}
     __device__ bool assess_feas(const double (&x)[2], double (&g)[2], Cut& cut) {
         const double fj = x[0] + x[1] - 3.0;
@@ -390,6 +400,7 @@ struct OrHalfPlane {  // tests/cutting_plane_tests.rs:12-28
 };
 
 struct OrAlwaysCut {  // tests/cutting_plane_tests.rs:33-42, 91-99, 104-122
+    static constexpr int kN = 2;
     __device__ void init(const BatchArgs&, long long) {}
     __device__ bool assess_feas(const double (&)[2], double (&g)[2], Cut& cut) {
         g[0] = 1.0; g[1] = 1.0; cut = single_cut(1.0);
@@ -408,6 +419,7 @@ struct OrAlwaysCut {  // tests/cutting_plane_tests.rs:33-42, 91-99, 104-122
 };
 
 struct OrOptimBox {  // tests/cutting_plane_tests.rs:47-73 (optim) and :197-264 (optim_q)
+    static constexpr int kN = 2;
     __device__ void init(const BatchArgs&, long long) {}
     __device__ bool assess_optim(const double (&x)[2], double& gamma, double (&g)[2], Cut& cut) {
         const double f0 = x[0] + x[1];
@@ -447,10 +459,104 @@ struct OrOptimBox {  // tests/cutting_plane_tests.rs:47-73 (optim) and :197-264 
     }
 };
 
+// tests/lmi_tests.rs:121-172 — MyLmiOracle: minimise c·x subject to L LMIs B_b - sum_k F_bk x_k >= 0, round-robin over the
+// L blocks and the objective cut.  One thread per problem: n = 3 variables, up to 3 blocks of size m <= 4; every block is
+// LMIOracle::assess_feas (src/oracles/lmi_oracle.rs:24-44) over LDLTMgr (src/oracles/ldlt_mgr.rs:29-55, 98-124), all in
+// local arrays.  table = c[3], then per block F_0, F_1, F_2 (m×m each), B (m×m); aux[0] = L, aux[1..L] = block sizes.
+struct OrLmiLinOpt {
+    static constexpr int kN = 3;
+    static constexpr int kMaxM = 4, kMaxBlocks = 3;
+    int idx, nblocks;
+    int msize[kMaxBlocks];
+    const double* fbase[kMaxBlocks];
+    const double* c;
+    __device__ void init(const BatchArgs& a, long long) {
+        idx = -1;
+        nblocks = a.aux[0];
+        c = a.table;
+        const double* t = a.table + kN;
+        for (int b = 0; b < kMaxBlocks; ++b) {
+            msize[b] = b < nblocks ? a.aux[1 + b] : 0;
+            fbase[b] = t;
+            t += (kN + 1) * msize[b] * msize[b];
+        }
+    }
+    // LMIOracle::assess_feas for block b: true if a cut (g, ep) was produced
+    __device__ bool block_feas(int b, const double (&x)[3], double (&g)[3], double& ep) const {
+        const int m = msize[b];
+        const double* F = fbase[b];
+        const double* B = F + kN * m * m;
+        double T[kMaxM * kMaxM];
+        double wit[kMaxM];
+        auto elem = [&](int i, int j) {   // lmi_oracle.rs:28-34
+            double s = B[i * m + j];
+            for (int k = 0; k < kN; ++k) s -= F[k * m * m + i * m + j] * x[k];
+            return s;
+        };
+        int pos = 0;
+        for (int i = 0; i < m; ++i) {      // ldlt_mgr.rs:29-55
+            double diag = elem(i, 0);
+            for (int j = 0; j < i; ++j) {
+                T[j * kMaxM + i] = diag;
+                T[i * kMaxM + j] = diag / T[j * kMaxM + j];
+                double sum = 0.0;
+                for (int k = 0; k <= j; ++k) sum += T[i * kMaxM + k] * T[k * kMaxM + (j + 1)];
+                diag = elem(i, j + 1) - sum;
+            }
+            T[i * kMaxM + i] = diag;
+            if (diag <= 0.0) { pos = i + 1; break; }
+        }
+        if (pos == 0) return false;
+        const int mm = pos - 1;             // witness, ldlt_mgr.rs:98-111
+        wit[mm] = 1.0;
+        for (int i = mm; i >= 1; --i) {
+            double sum = 0.0;
+            for (int k = i; k < pos; ++k) sum += T[k * kMaxM + (i - 1)] * wit[k];
+            wit[i - 1] = -sum;
+        }
+        ep = -T[mm * kMaxM + mm];
+        for (int k = 0; k < kN; ++k) {      // sym_quad, ldlt_mgr.rs:115-124
+            double r = 0.0;
+            for (int i = 0; i < pos; ++i)
+                for (int j = 0; j < pos; ++j) r += wit[i] * F[k * m * m + i * m + j] * wit[j];
+            g[k] = r;
+        }
+        return true;
+    }
+    __device__ bool assess_optim(const double (&x)[3], double& gamma, double (&g)[3], Cut& cut) {
+        double f0 = 0.0;                    // self.c.dot(xc)
+        for (int k = 0; k < kN; ++k) f0 += c[k] * x[k];
+        const int nc = nblocks + 1;
+        for (int t = 0; t < nc; ++t) {
+            idx = (idx == nc - 1) ? 0 : idx + 1;
+            if (idx < nblocks) {
+                double ep;
+                if (block_feas(idx, x, g, ep)) { cut = single_cut(ep); return false; }
+            } else {
+                const double fj = f0 - gamma;
+                if (fj > 0.0) {
+                    for (int k = 0; k < kN; ++k) g[k] = c[k];
+                    cut = single_cut(fj);
+                    return false;
+                }
+                gamma = f0;
+            }
+        }
+        for (int k = 0; k < kN; ++k) g[k] = c[k];
+        cut = single_cut(0.0);
+        return true;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ kernel
-template <class Space, class Oracle, int MODE>
+template <int N>
+__device__ __forceinline__ void copy_vec(double (&dst)[N], const double (&src)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = src[i];
+}
+
+template <int N, class Space, class Oracle, int MODE>
 __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
-    constexpr int N = 2;
     const CalcConsts cc = CalcConsts::make(N, a.use_parallel_cut);
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -480,7 +586,9 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
             om.init(a, pid);
 
             bool has_best = false;
-            double best[N] = {0.0, 0.0};
+            double best[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) best[i] = 0.0;
             long long niter = 0;
             int exit_status = kExitMaxIt;
             double g[N];
@@ -491,7 +599,7 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
                     int status;
                     if (shrunk) {
                         has_best = true;
-                        best[0] = sp.xc[0]; best[1] = sp.xc[1];
+                        copy_vec<N>(best, sp.xc);
                         status = sp.update(cc, kCentral, g, cut);
                     } else {
                         status = sp.update(cc, kBias, g, cut);
@@ -503,7 +611,7 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
                 for (; niter < a.max_iters; ++niter) {
                     if (!om.assess_feas(sp.xc, g, cut)) {
                         has_best = true;
-                        best[0] = sp.xc[0]; best[1] = sp.xc[1];
+                        copy_vec<N>(best, sp.xc);
                         exit_status = kExitFeasible;
                         break;
                     }
@@ -532,14 +640,14 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
                         if (status != kSuccess || trial.tsq < a.tolerance) break;
                     }
                     if (feasible) {
-                        sp.xc[0] = trial.xc[0]; sp.xc[1] = trial.xc[1];   // self.space.set_xc(x)
+                        copy_vec<N>(sp.xc, trial.xc);   // self.space.set_xc(x)
                         upper = gm;
                     } else {
                         lower = gm;
                     }
                 }
                 has_best = upper != u_orig;
-                best[0] = sp.xc[0]; best[1] = sp.xc[1];
+                copy_vec<N>(best, sp.xc);
                 gamma = upper;
             } else {  // optim_q :331-374
                 bool retry = false;
@@ -549,7 +657,7 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
                     const bool shrunk = om.assess_optim_q(sp.xc, gamma, retry, g, cut, xq, more_alt);
                     if (shrunk) {
                         has_best = true;
-                        best[0] = xq[0]; best[1] = xq[1];
+                        copy_vec<N>(best, xq);
                         retry = false;
                     }
                     const int status = sp.update(cc, kQ, g, cut);
@@ -568,11 +676,17 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
             a.num_iters[pid] = niter;
             a.exit_status[pid] = exit_status;
             if (a.has_xbest) a.has_xbest[pid] = has_best ? 1 : 0;
-            if (a.xbest && has_best) { a.xbest[pid * N] = best[0]; a.xbest[pid * N + 1] = best[1]; }
+            if (a.xbest && has_best) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) a.xbest[pid * N + i] = best[i];
+            }
             if (a.gamma) a.gamma[pid] = gamma;
             if (a.tsq) a.tsq[pid] = sp.tsq;
             if (a.kappa) a.kappa[pid] = sp.kappa;
-            if (a.xc) { a.xc[pid * N] = sp.xc[0]; a.xc[pid * N + 1] = sp.xc[1]; }
+            if (a.xc) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) a.xc[pid * N + i] = sp.xc[i];
+            }
         }
     }
 }
@@ -584,10 +698,11 @@ int launch_kind(const BatchArgs& a, cudaStream_t s, int sm_count) {
     const long long cap = (long long)sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    constexpr int N = Oracle::kN;
     if (a.kind == ELL_KIND_ELLSTABLE)
-        batch_small_kernel<EllStableReg<2>, Oracle, MODE><<<(unsigned)blocks, 128, 0, s>>>(a);
+        batch_small_kernel<N, EllStableReg<N>, Oracle, MODE><<<(unsigned)blocks, 128, 0, s>>>(a);
     else
-        batch_small_kernel<EllReg<2>, Oracle, MODE><<<(unsigned)blocks, 128, 0, s>>>(a);
+        batch_small_kernel<N, EllReg<N>, Oracle, MODE><<<(unsigned)blocks, 128, 0, s>>>(a);
     ELL_CUDA_TRY(cudaGetLastError());
     return ELLCUDA_OK;
 }
@@ -606,8 +721,23 @@ int launch_math_probe(int which, const double* x, double* y, long long n, cudaSt
 }
 
 int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
-    if (a.n != 2) { set_error("this oracle is defined for n = 2"); return ELLCUDA_E_ARG; }
     const int m = a.mode;
+    if (oracle_id == ELL_ORACLE_LMI_LINOPT) {
+        if (a.n != 3 || m != ELL_MODE_OPTIM || !a.table || a.aux[0] < 1 || a.aux[0] > OrLmiLinOpt::kMaxBlocks) {
+            set_error("LMI_LINOPT on the device: n = 3, cutting_plane_optim, 1..3 blocks of size <= 4");
+            return ELLCUDA_E_ARG;
+        }
+        long long need = 3;
+        for (int b = 0; b < a.aux[0]; ++b) {
+            if (a.aux[1 + b] < 1 || a.aux[1 + b] > OrLmiLinOpt::kMaxM) { set_error("LMI_LINOPT: block size must be 1..4"); return ELLCUDA_E_ARG; }
+            need += 4LL * a.aux[1 + b] * a.aux[1 + b];
+        }
+        if (a.table_len < need) { set_error("LMI_LINOPT: table too short"); return ELLCUDA_E_ARG; }
+        const int rc = launch_kind<OrLmiLinOpt, ELL_MODE_OPTIM>(a, s, sm_count);
+        if (rc == ELLCUDA_OK && launches) *launches += 1;
+        return rc;
+    }
+    if (a.n != 2) { set_error("this oracle is defined for n = 2"); return ELLCUDA_E_ARG; }
     int rc = ELLCUDA_E_ARG;
 #define ELL_CASE(ID, OR, MODE) \
     if (oracle_id == (ID) && m == (MODE)) { rc = launch_kind<OR, MODE>(a, s, sm_count); goto done; }

@@ -221,7 +221,6 @@ static int batch_solve_impl(const ell_batch_desc* d, const ell_batch_result* r) 
             rc = launch_batch_warp(a, d->oracle_id, s, di->sm_count, &g_last_launches);
             break;
         case ELL_ORACLE_LMI:
-        case ELL_ORACLE_LMI_LINOPT:
             rc = launch_batch_stable(a, d->oracle_id, s, di->sm_count, &g_last_launches);
             break;
         default:

@@ -353,3 +353,20 @@ def test_full_size_bowl_one_million(ref):
     r = ref.solve(sub)
     assert np.array_equal(g.num_iters[idx], r.num_iters) and np.array_equal(g.exit_status[idx], r.exit_status)
     assert np.array_equal(g.xc[idx], r.xc) and np.array_equal(g.gamma[idx], r.gamma) and np.array_equal(g.kappa[idx], r.kappa)
+
+
+def test_lmi_tests_rs_fixture_on_device(ref):
+    """tests/lmi_tests.rs:121-225 (MyLmiOracle over two LMIOracle blocks, cutting_plane_optim) with Ell and EllStable:
+    the reference asserts < 300 / < 400 iterations; the checker gives 11 / 21 and these gammas."""
+    from test_oracle_pins import LMI_TAB
+    for kind, iters, gamma in ((A.KIND_ELL, 11, -3.7502205782089257), (A.KIND_ELLSTABLE, 21, -3.5724046875091333)):
+        prob = BatchProblem(oracle_id=A.ORACLE_LMI_LINOPT, n=3, count=2, kind=kind, kappa0=10.0, gamma0=math.inf, table=LMI_TAB,
+                            aux=[2, 2, 3])
+        g, r = both(ref, prob)
+        assert g.has_xbest.all() and (g.num_iters == iters).all() and (g.gamma == gamma).all()
+        assert_parity(g, r, exact=True, what=f"lmi_tests.rs kind={kind}")
+    rng = np.random.default_rng(2)
+    prob = BatchProblem(oracle_id=A.ORACLE_LMI_LINOPT, n=3, count=300, kappa0=rng.uniform(5, 50, 300),
+                        xc0=rng.uniform(-1, 1, (300, 3)), gamma0=math.inf, table=LMI_TAB, aux=[2, 2, 3])
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what="lmi_tests.rs random starts")
