@@ -159,8 +159,8 @@ __device__ __forceinline__ double seq_sum_pair(double* s, double lo, double hi, 
 }
 
 template <bool DIAG>
-__device__ int stable_update(const CalcConsts& cc, const WarpMem& wm, int lane, int n, double g0, double g1, const Cut& cut,
-                             double& d0, double& d1, double& xc0, double& xc1, double& kappa, double& tsq) {
+__device__ int stable_update(const CalcConsts& cc, int which, const WarpMem& wm, int lane, int n, double g0, double g1,
+                             const Cut& cut, double& d0, double& d1, double& xc0, double& xc1, double& kappa, double& tsq) {
     const int i0 = lane, i1 = lane + 32;
     const bool on0 = i0 < n, on1 = i1 < n;
     // --- inv(L)*grad (src/ell_stable.rs:60-69)
@@ -181,7 +181,7 @@ __device__ int stable_update(const CalcConsts& cc, const WarpMem& wm, int lane, 
     const double omega = seq_sum_pair(wm.sv, on0 ? gg0 : 0.0, on1 ? gg1 : 0.0, lane, n);   // sv now holds gg[]
     tsq = kappa * omega;
     Rsd r;
-    const int status = ell_calc(cc, kBias, cut, tsq, r);
+    const int status = ell_calc(cc, which, cut, tsq, r);
     if (status != kSuccess) return status;
     // --- mq*grad = inv(L')*inv(D)*inv(L)*grad (:93-98): q[c] = z[c] - sum_{j>c, ascending} (Q[c][j]*w[c])*q[j]
     double q0 = z0, q1 = z1;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, i
                 exit_status = kExitFeasible;
                 break;
             }
-            const int status = stable_update<DIAG>(cc, wm, lane, n, g0, g1, single_cut(ep), d0, d1, xc0, xc1, kappa, tsq);
+            const int status = stable_update<DIAG>(cc, kBias, wm, lane, n, g0, g1, single_cut(ep), d0, d1, xc0, xc1, kappa, tsq);
             if (status != kSuccess) { exit_status = status; break; }
             if (tsq < a.tolerance) { exit_status = kExitTol; break; }
         }
@@ -342,7 +342,50 @@ __global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------- single EllStable handle
+// One EllStable (n <= 64) driven call by call from the host (SearchSpace on EllStable, src/ell_stable.rs:128-210): one warp
+// loads the packed upper triangle, runs the literal update_core recurrence (GENERAL variant above) and stores it back.
+__global__ void __launch_bounds__(32) stable_single_kernel(double* __restrict__ qu_g, double* __restrict__ xc_g, double* __restrict__ scal,
+                                                           int* __restrict__ status_out, const double* __restrict__ g, int n,
+                                                           CalcConsts cc, int which, Cut cut) {
+    __shared__ double s_qu[kNMax * (kNMax + 1) / 2];
+    __shared__ double s_vec[3 * kNMax];
+    const int lane = threadIdx.x;
+    const int tri = n * (n + 1) / 2;
+    for (int e = lane; e < tri; e += 32) s_qu[e] = qu_g[e];
+    __syncwarp();
+    WarpMem wm;
+    wm.sx = nullptr; wm.sa = nullptr; wm.st = nullptr; wm.swit = nullptr;
+    wm.sv = s_vec; wm.sw = s_vec + kNMax; wm.sz = s_vec + 2 * kNMax; wm.qu = s_qu;
+    const int i0 = lane, i1 = lane + 32;
+    const bool on0 = i0 < n, on1 = i1 < n;
+    double g0 = on0 ? g[i0] : 0.0, g1 = on1 ? g[i1] : 0.0;
+    double xc0 = on0 ? xc_g[i0] : 0.0, xc1 = on1 ? xc_g[i1] : 0.0;
+    double kappa = scal[0], tsq = scal[1];
+    double d0 = 0.0, d1 = 0.0;
+    const int status = stable_update<false>(cc, which, wm, lane, n, g0, g1, cut, d0, d1, xc0, xc1, kappa, tsq);
+    __syncwarp();
+    if (status == kSuccess) {
+        for (int e = lane; e < tri; e += 32) qu_g[e] = s_qu[e];
+        if (on0) xc_g[i0] = xc0;
+        if (on1) xc_g[i1] = xc1;
+    }
+    if (lane == 0) {
+        scal[0] = kappa;   // unchanged on a failed cut
+        scal[1] = tsq;     // tsq survives a failed cut (src/ell_stable.rs:85-90)
+        *status_out = status;
+    }
+}
+
 }  // namespace
+
+int launch_stable_single(double* qu, double* xc, double* scal, int* status, const double* g, int n, int use_parallel_cut, int which,
+                         const Cut& cut, cudaStream_t s) {
+    const CalcConsts cc = CalcConsts::make(n, use_parallel_cut);
+    stable_single_kernel<<<1, 32, 0, s>>>(qu, xc, scal, status, g, n, cc, which, cut);
+    ELL_CUDA_TRY(cudaGetLastError());
+    return ELLCUDA_OK;
+}
 
 int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     if (oracle_id != ELL_ORACLE_LMI) { set_error("this oracle has no device implementation yet"); return ELLCUDA_E_ARG; }

@@ -72,6 +72,8 @@ struct DevGuard {
 int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 int launch_math_probe(int which, const double* x_dev, double* y_dev, long long n, cudaStream_t s);
+int launch_stable_single(double* qu_packed_upper, double* xc, double* scal_kappa_tsq, int* status, const double* g, int n,
+                         int use_parallel_cut, int which, const Cut& cut, cudaStream_t s);
 int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 
 }  // namespace ellcuda

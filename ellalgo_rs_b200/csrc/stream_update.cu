@@ -543,6 +543,10 @@ constexpr size_t sweep_smem(int rows, int stages) { return (size_t)stages * (kCo
 
 // =================================================================================================== handle
 struct ellcuda_ctx {
+    int kind = ELL_KIND_ELL;    // ELL_KIND_ELLSTABLE handles (n <= 64) use only the `st_*` members, xc, gstage, status_host
+    double* st_qu = nullptr;    // EllStable: packed upper triangle incl. diagonal, n(n+1)/2
+    double* st_scal = nullptr;  // EllStable: {kappa, tsq}
+    int* st_status = nullptr;   // EllStable: CutStatus of the last update
     int device = 0;
     long long n = 0, w = 0, c0 = 0, ld = 0, npad = 0, ld_part = 0, ncb = 0;
     int nseg = 1, reduce_mode = 0, no_defer = 0, use_parallel = 1;
@@ -580,6 +584,7 @@ namespace {
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
     DevGuard guard(h->device);
+    cudaFree(h->st_qu); cudaFree(h->st_scal); cudaFree(h->st_status);
     cudaFree(h->S); cudaFree(h->xc); cudaFree(h->gpad); cudaFree(h->gzero); cudaFree(h->gstage); cudaFreeHost(h->status_host);
     cudaFree(h->pend); cudaFree(h->partial); cudaFree(h->block_omega); cudaFree(h->counters); cudaFree(h->sc);
     for (int r = 0; r < kMaxRanks; ++r)
@@ -706,11 +711,58 @@ int flush_pending(ellcuda_ctx* h) {  // make S hold the reference's `mq` exactly
 using namespace ellcuda;
 
 extern "C" {
+// ---- EllStable as a single host-driven search space (src/ell_stable.rs:9-35, 128-210), n <= 64 -------------------------
+static int create_stable(const ell_create_desc* d, ell_handle* out) {
+    if (d->n > 64) { set_error("a single EllStable handle supports n <= 64 (its recurrences do not stream; use batched mode)"); return ELLCUDA_E_ARG; }
+    if ((d->row_begin != 0 || (d->row_end != 0 && d->row_end != d->n))) { set_error("EllStable does not shard"); return ELLCUDA_E_ARG; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (libellcuda has no CPU fallback)");
+        return ELLCUDA_E_CUDA;
+    }
+    if (d->device < 0 || d->device >= count) { set_error("device ordinal out of range"); return ELLCUDA_E_ARG; }
+    cudaDeviceProp prop;
+    ELL_CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major < 10) { set_error("libellcuda is built for sm_100a (B200) only"); return ELLCUDA_E_CUDA; }
+    ELL_DEVICE_SCOPE(d->device);
+    const long long n = d->n, tri = n * (n + 1) / 2;
+    ellcuda_ctx* h = new ellcuda_ctx();
+    h->kind = ELL_KIND_ELLSTABLE;
+    h->device = d->device; h->n = n; h->w = n; h->use_parallel = d->use_parallel_cut;
+    if (d->stream) h->stream = (cudaStream_t)d->stream;
+    else {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+        h->own_stream = true;
+    }
+    std::vector<double> qu((size_t)tri, 0.0);   // strict upper = L-factor entries, diagonal = D (src/ell_stable.rs:52-125)
+    for (long long r = 0, e = 0; r < n; ++r)
+        for (long long c = r; c < n; ++c, ++e)
+            qu[e] = d->mq ? d->mq[r * n + c] : (r == c ? (d->diag ? d->diag[r] : 1.0) : 0.0);
+    const double scal[2] = {d->kappa, 0.0};
+    cudaError_t e = cudaMalloc(&h->st_qu, (size_t)tri * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&h->st_scal, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->st_status, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&h->xc, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&h->gstage, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->status_host, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->st_qu, qu.data(), (size_t)tri * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->st_scal, scal, 16, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->st_status, 0, sizeof(int), h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->xc, d->xc, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { free_ctx(h); return cuda_fail(e, "ellcuda_create (EllStable)", __FILE__, __LINE__); }
+    *out = h;
+    return ELLCUDA_OK;
+}
+
 int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     if (!d || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
     *out = nullptr;
-    if (d->kind != ELL_KIND_ELL) { set_error("large-n mode exists for Ell only (EllStable does not shard; use batched mode)"); return ELLCUDA_E_ARG; }
+    if (d->kind != ELL_KIND_ELL && d->kind != ELL_KIND_ELLSTABLE) { set_error("bad kind"); return ELLCUDA_E_ARG; }
     if (d->n <= 0 || !d->xc) { set_error("n must be positive and xc given"); return ELLCUDA_E_ARG; }
+    if (d->kind == ELL_KIND_ELLSTABLE) return create_stable(d, out);
     long long rb = d->row_begin, re = d->row_end;
     if (rb == 0 && re == 0) re = d->n;
     if (rb < 0 || re > d->n || rb >= re) { set_error("bad row range"); return ELLCUDA_E_ARG; }
@@ -779,6 +831,29 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
 int ellcuda_clone(ell_handle h, ell_handle* out) {
     if (!h || !out) { set_error("null handle"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
+    if (h->kind == ELL_KIND_ELLSTABLE) {
+        const long long n = h->n, tri = n * (n + 1) / 2;
+        ellcuda_ctx* c = new ellcuda_ctx();
+        c->kind = h->kind; c->device = h->device; c->n = n; c->w = n; c->use_parallel = h->use_parallel;
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+        c->own_stream = true;
+        e = cudaMalloc(&c->st_qu, (size_t)tri * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&c->st_scal, 16);
+        if (e == cudaSuccess) e = cudaMalloc(&c->st_status, sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&c->xc, (size_t)n * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&c->gstage, (size_t)n * 8);
+        if (e == cudaSuccess) e = cudaMallocHost(&c->status_host, sizeof(int));
+        cudaStream_t s = h->stream;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->st_qu, h->st_qu, (size_t)tri * 8, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->st_scal, h->st_scal, 16, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->st_status, h->st_status, sizeof(int), cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->xc, h->xc, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { free_ctx(c); return cuda_fail(e, "ellcuda_clone (EllStable)", __FILE__, __LINE__); }
+        *out = c;
+        return ELLCUDA_OK;
+    }
     ellcuda_ctx* c = new ellcuda_ctx();
     c->device = h->device; c->n = h->n; c->w = h->w; c->c0 = h->c0;
     c->nseg = h->nseg; c->reduce_mode = h->reduce_mode; c->no_defer = h->no_defer; c->use_parallel = h->use_parallel;
@@ -829,8 +904,18 @@ static int read_scal(ell_handle h, Scal* sc) {
     return ELLCUDA_OK;
 }
 
+static int read_stable_scal(ell_handle h, int which, double* out) {
+    ELL_DEVICE_SCOPE(h->device);
+    double v[2];
+    ELL_CUDA_TRY(cudaMemcpyAsync(v, h->st_scal, 16, cudaMemcpyDeviceToHost, h->stream));
+    ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *out = v[which];
+    return ELLCUDA_OK;
+}
+
 int ellcuda_tsq(ell_handle h, double* out) {
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (h->kind == ELL_KIND_ELLSTABLE) return read_stable_scal(h, 1, out);
     Scal sc;
     int rc = read_scal(h, &sc);
     if (rc) return rc;
@@ -840,6 +925,7 @@ int ellcuda_tsq(ell_handle h, double* out) {
 
 int ellcuda_kappa(ell_handle h, double* out) {
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (h->kind == ELL_KIND_ELLSTABLE) return read_stable_scal(h, 0, out);
     Scal sc;
     int rc = read_scal(h, &sc);
     if (rc) return rc;
@@ -850,6 +936,15 @@ int ellcuda_kappa(ell_handle h, double* out) {
 int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row-major
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
+    if (h->kind == ELL_KIND_ELLSTABLE) {   // the factor: diagonal + strict upper; the strict lower (scratch in the reference) is 0
+        const long long n = h->n, tri = n * (n + 1) / 2;
+        std::vector<double> qu((size_t)tri);
+        ELL_CUDA_TRY(cudaMemcpyAsync(qu.data(), h->st_qu, (size_t)tri * 8, cudaMemcpyDeviceToHost, h->stream));
+        ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (long long r = 0, e = 0; r < n; ++r)
+            for (long long c = 0; c < n; ++c) out[r * n + c] = c >= r ? qu[e++] : 0.0;
+        return ELLCUDA_OK;
+    }
     Scal sc;
     int rc = read_scal(h, &sc);
     if (rc) return rc;
@@ -873,11 +968,17 @@ int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, do
     ELL_DEVICE_SCOPE(h->device);
     h->which = which;
     h->cut = has_beta1 > 0 ? parallel_cut(beta0, beta1) : single_cut(beta0);
+    if (h->kind == ELL_KIND_ELLSTABLE) {   // the whole update_core is one single-warp kernel; finish has nothing left to do
+        h->launches += 1;
+        return launch_stable_single(h->st_qu, h->xc, h->st_scal, h->st_status, grad_dev, (int)h->n, h->use_parallel, which, h->cut,
+                                    h->stream);
+    }
     return enqueue_begin(h, grad_dev);
 }
 
 int ellcuda_update_finish(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    if (h->kind == ELL_KIND_ELLSTABLE) return ELLCUDA_OK;
     ELL_DEVICE_SCOPE(h->device);
     if (!h->gsrc) { set_error("ellcuda_update_finish without ellcuda_update_begin"); return ELLCUDA_E_ARG; }
     const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
@@ -902,13 +1003,14 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double 
     return ellcuda_last_status(h, out_status);
 }
 
-double* ellcuda_grad_t_ptr(ell_handle h) { return h ? h->xblk : nullptr; }
-int32_t* ellcuda_status_ptr(ell_handle h) { return h ? &h->sc->status : nullptr; }
+double* ellcuda_grad_t_ptr(ell_handle h) { return h && h->kind == ELL_KIND_ELL ? h->xblk : nullptr; }
+int32_t* ellcuda_status_ptr(ell_handle h) { return !h ? nullptr : h->kind == ELL_KIND_ELLSTABLE ? h->st_status : &h->sc->status; }
 
 int ellcuda_last_status(ell_handle h, int32_t* out_status) {
     if (!h || !out_status) { set_error("null argument"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
-    ELL_CUDA_TRY(cudaMemcpyAsync(h->status_host, &h->sc->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    const int* src = h->kind == ELL_KIND_ELLSTABLE ? h->st_status : &h->sc->status;
+    ELL_CUDA_TRY(cudaMemcpyAsync(h->status_host, src, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     *out_status = *h->status_host;
     return ELLCUDA_OK;
@@ -916,6 +1018,7 @@ int ellcuda_last_status(ell_handle h, int32_t* out_status) {
 
 int ellcuda_exchange_export(ell_handle h, void* handle_out) {
     if (!h || !handle_out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (h->kind != ELL_KIND_ELL) { set_error("EllStable does not shard"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
     cudaIpcMemHandle_t ipc;
     static_assert(sizeof(ipc) == ELLCUDA_IPC_HANDLE_BYTES, "IPC handle size");
@@ -935,6 +1038,7 @@ static int attach_common(ell_handle h, int32_t nranks, int32_t rank) {
 
 int ellcuda_exchange_attach_ptrs(ell_handle h, int32_t nranks, int32_t rank, void* const* blocks) {
     if (!h || !blocks) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (h->kind != ELL_KIND_ELL) { set_error("EllStable does not shard"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
     int rc = attach_common(h, nranks, rank);
     if (rc) return rc;
@@ -948,6 +1052,7 @@ int ellcuda_exchange_attach_ptrs(ell_handle h, int32_t nranks, int32_t rank, voi
 
 int ellcuda_exchange_attach(ell_handle h, int32_t nranks, int32_t rank, const void* handles) {
     if (!h || !handles) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (h->kind != ELL_KIND_ELL) { set_error("EllStable does not shard"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
     int rc = attach_common(h, nranks, rank);
     if (rc) return rc;

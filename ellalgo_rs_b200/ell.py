@@ -31,6 +31,8 @@ class _DevVec:
 
 
 class Ell:
+    KIND = _abi.KIND_ELL
+
     def __init__(self, kappa, xc, mq=None, diag=None, *, device=0, no_defer_trick=False, use_parallel_cut=True,
                  rows=None, reduce_mode=0, stream=0, _handle=None):
         self._keep = []
@@ -40,7 +42,7 @@ class Ell:
         xc = np.ascontiguousarray(xc, dtype=np.float64)
         n = xc.shape[0]
         d = _abi.CreateDesc()
-        d.kind, d.device, d.n, d.kappa = _abi.KIND_ELL, device, n, float(kappa)
+        d.kind, d.device, d.n, d.kappa = self.KIND, device, n, float(kappa)
         if mq is not None:
             mq = np.ascontiguousarray(mq, dtype=np.float64)
             if mq.shape != (n, n):
@@ -92,7 +94,7 @@ class Ell:
     def clone(self):  # #[derive(Clone)]
         h = C.c_void_p()
         check(lib().ellcuda_clone(self._h, C.byref(h)))
-        e = Ell(0, None, _handle=h)
+        e = type(self)(0, None, _handle=h)
         e.n, e.rows, e.no_defer_trick = self.n, self.rows, self.no_defer_trick
         return e
 
@@ -194,3 +196,12 @@ class Ell:
     @property
     def launches(self) -> int:
         return int(lib().ellcuda_handle_launch_count(self._h))
+
+
+class EllStable(Ell):
+    """Host mirror of the reference's `EllStable` (src/ell_stable.rs) as a single host-driven search space, n <= 64:
+    `new`, `new_with_scalar`, `new_with_matrix` (:18-35) and the SearchSpace methods (:128-166); update_core (:52-125)
+    runs as one single-warp kernel per call.  `mq` returns the factor (diagonal + strict upper triangle)."""
+    KIND = _abi.KIND_ELLSTABLE
+
+    from_covariance = None   # the reference's EllStable has no such constructor

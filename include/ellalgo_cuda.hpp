@@ -66,9 +66,12 @@ struct EllConfig {
     int reduce_mode = 0;            // 0 = bit-identical to the reference's summation order
 };
 
-// The reference's `Ell` with its matrix in B200 HBM.  Copying clones the device state (#[derive(Clone)], src/ell.rs:8).
-class EllCuda {
+// The reference's `Ell` (KIND = ELL_KIND_ELL, src/ell.rs) with its matrix in B200 HBM, or `EllStable`
+// (KIND = ELL_KIND_ELLSTABLE, src/ell_stable.rs, n <= 64).  Copying clones the device state (#[derive(Clone)]).
+template <int KIND>
+class EllCudaT {
   public:
+    using EllCuda = EllCudaT;   // the constructors below are written once for both kinds
     using Config = EllConfig;
     static EllCuda new_with_matrix(double kappa, const Arr& mq, const Arr& xc, Config cfg = {}) {  // src/ell.rs:31-41
         if (mq.size() != xc.size() * xc.size()) throw std::invalid_argument("mq must be n x n");
@@ -84,10 +87,10 @@ class EllCuda {
     static EllCuda from_covariance(const Arr& cov, const Arr& xc, Config cfg = {}) {  // src/ell.rs:76-78
         return new_with_matrix(1.0, cov, xc, cfg);
     }
-    EllCuda(const EllCuda& o) : n_(o.n_) { check(ellcuda_clone(o.h_, &h_)); }
-    EllCuda(EllCuda&& o) noexcept : h_(o.h_), n_(o.n_) { o.h_ = nullptr; }
+    EllCudaT(const EllCudaT& o) : n_(o.n_) { check(ellcuda_clone(o.h_, &h_)); }
+    EllCudaT(EllCudaT&& o) noexcept : h_(o.h_), n_(o.n_) { o.h_ = nullptr; }
     EllCuda& operator=(EllCuda o) noexcept { std::swap(h_, o.h_); std::swap(n_, o.n_); return *this; }
-    ~EllCuda() { if (h_) ellcuda_destroy(h_); }
+    ~EllCudaT() { if (h_) ellcuda_destroy(h_); }
 
     // ---- SearchSpace (src/cutting_plane.rs:154-182)
     Arr xc() const { Arr x(n_); check(ellcuda_xc(h_, x.data())); return x; }
@@ -106,9 +109,9 @@ class EllCuda {
     ell_handle handle() const { return h_; }
 
   private:
-    EllCuda(double kappa, const Arr* mq, const Arr* diag, const Arr& xc, Config cfg) : n_(xc.size()) {
+    EllCudaT(double kappa, const Arr* mq, const Arr* diag, const Arr& xc, Config cfg) : n_(xc.size()) {
         ell_create_desc d{};
-        d.kind = ELL_KIND_ELL; d.device = cfg.device; d.n = static_cast<int64_t>(n_); d.kappa = kappa;
+        d.kind = KIND; d.device = cfg.device; d.n = static_cast<int64_t>(n_); d.kappa = kappa;
         d.mq = mq ? mq->data() : nullptr; d.diag = diag ? diag->data() : nullptr; d.xc = xc.data();
         d.no_defer_trick = cfg.no_defer_trick; d.use_parallel_cut = cfg.use_parallel_cut;
         d.row_begin = 0; d.row_end = static_cast<int64_t>(n_); d.reduce_mode = cfg.reduce_mode; d.stream = nullptr;
@@ -124,6 +127,8 @@ class EllCuda {
     ell_handle h_ = nullptr;
     std::size_t n_ = 0;
 };
+using EllCuda = EllCudaT<ELL_KIND_ELL>;
+using EllStableCuda = EllCudaT<ELL_KIND_ELLSTABLE>;   // from_covariance is Ell's only; mq() returns the factor
 
 // ---- drivers (generic over any Space with the SearchSpace methods, any Oracle with the trait's method)
 template <class Oracle, class Space>

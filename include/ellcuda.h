@@ -96,7 +96,8 @@ extern "C" {
 #define ELL_ORACLE_OPTIM_BOX   14 /* tests/cutting_plane_tests.rs:47-73  optim n=2          */
 #define ELL_ORACLE_LMI_LINOPT  15 /* tests/lmi_tests.rs:121-172 MyLmiOracle: min c·x over L
                                      LMI blocks, round-robin.  table = c[n], then per block
-                                     F_0..F_{n-1}, B;  aux[0] = L, aux[1..L] = block sizes  */
+                                     F_0..F_{n-1}, B;  aux[0] = L, aux[1..L] = block sizes
+                                     (device: n = 3, L <= 3, block size <= 4)               */
 #define ELL_ORACLE_COUNT       16
 
 /* ======================================================================================= *
@@ -174,8 +175,11 @@ int32_t ellcuda_lowpass_band_edge(int32_t n, double w);
 typedef struct ellcuda_ctx* ell_handle;
 
 typedef struct ell_create_desc {
-    int32_t kind;              /* ELL_KIND_ELL (ELLSTABLE has no large-n form: its
-                                  triangular recurrences do not shard, use batched mode)  */
+    int32_t kind;              /* ELL_KIND_ELL: any n, matrix streamed from HBM, optionally row-sharded.
+                                  ELL_KIND_ELLSTABLE (src/ell_stable.rs): n <= 64, whole matrix, `mq` = the
+                                  factor as the reference holds it (diagonal + strict upper triangle are
+                                  read; need not be symmetric); its triangular recurrences neither stream
+                                  nor shard — large batches go through ellcuda_batch_solve               */
     int32_t device;
     int64_t n;
     double  kappa;             /* Ell::new_with_scalar(kappa,…) / new_with_matrix(kappa,…) */

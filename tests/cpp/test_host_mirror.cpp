@@ -155,6 +155,41 @@ int main(int argc, char** argv) {
         try { ellip.update_bias_cut(std::make_pair(Arr(5, 0.5), SingleCut{0.0})); } catch (const std::invalid_argument&) { threw = true; }
         EXPECT(threw);  // the reference panics on a shape mismatch (src/arr.rs:427-429)
     }
+    {   // quasicvx::test_feasible (Ell, 35 iterations) and ::test_feasible_stable (EllStable), src/quasicvx.rs:61-105
+        struct Quasicvx {
+            int idx = -1;
+            std::pair<std::pair<Arr, SingleCut>, bool> assess_optim(const Arr& xc, double& gamma) {
+                const double sqrtx = xc[0], logy = xc[1];
+                for (int k = 0; k < 2; ++k) {
+                    idx = idx == 1 ? 0 : idx + 1;
+                    const double fv = idx == 0 ? sqrtx * sqrtx - logy : -sqrtx + gamma * std::exp(logy);
+                    if (fv > 0.0) {
+                        const Arr g = idx == 0 ? Arr{2.0 * sqrtx, -1.0} : Arr{-1.0, gamma * std::exp(logy)};
+                        return {{g, SingleCut{fv}}, false};
+                    }
+                }
+                gamma = sqrtx / std::exp(logy);
+                return {{{-1.0, sqrtx}, SingleCut{0.0}}, true};
+            }
+        };
+        Options o; o.tolerance = 1e-8;
+        auto ell = EllCuda::new_({10.0, 10.0}, {0.0, 0.0});
+        Quasicvx q1;
+        double gamma = 0.0;
+        auto [x, niter] = cutting_plane_optim(q1, ell, gamma, o);
+        EXPECT(x.has_value() && niter == 35);
+        EXPECT((*x)[0] * (*x)[0] >= 0.49 && (*x)[0] * (*x)[0] <= 0.51 && std::exp((*x)[1]) >= 1.6 && std::exp((*x)[1]) <= 1.7);
+        auto stable = EllStableCuda::new_({10.0, 10.0}, {0.0, 0.0});
+        Quasicvx q2;
+        double gamma2 = 0.0;
+        auto [xs, niter_s] = cutting_plane_optim(q2, stable, gamma2, o);
+        EXPECT(xs.has_value());
+        EXPECT(niter_s == 49);   // not pinned by the reference; value of the CPU restatement
+        auto inf = EllStableCuda::new_with_scalar(10.0, {100.0, 100.0});
+        Quasicvx q3;
+        double gamma3 = 0.0;
+        EXPECT(!cutting_plane_optim(q3, inf, gamma3, Options{}).first.has_value());
+    }
     std::printf("host mirror: all reference driver tests passed on the GPU search space\n");
     return 0;
 }

@@ -302,3 +302,71 @@ def test_large_n_against_checker(ref, n, mode):
     else:
         assert np.abs(got - mq).max() <= REL_TOL
     assert np.array_equal(got, got.T)  # stays bitwise symmetric, like the reference's mirrored writes
+
+
+# ---------------------------------------------------------------- EllStable as a single host-driven search space
+def test_ellstable_known_answers():  # src/ell_stable.rs:225-298
+    from ellalgo_rs_b200.ell import EllStable
+    g = 0.5 * np.ones(4)
+    e = EllStable.new_with_scalar(0.01, np.zeros(4))
+    assert e.kappa == 0.01 and e.tsq() == 0.0 and np.array_equal(e.xc(), np.zeros(4))
+    assert e.update_central_cut((g, SingleCut(0.0))) == CutStatus.Success
+    assert np.array_equal(e.xc(), -0.01 * np.ones(4)) and e.kappa == pytest.approx(0.16 / 15, abs=1e-6)
+    assert e.tsq() == pytest.approx(0.01, abs=1e-6)
+    e = EllStable.new_with_scalar(0.01, np.zeros(4))
+    assert e.update_bias_cut((g, SingleCut(0.05))) == CutStatus.Success
+    assert e.xc()[0] == pytest.approx(-0.03, abs=1e-6) and e.kappa == pytest.approx(0.008, abs=1e-6)
+    e = EllStable.new_with_scalar(0.01, np.zeros(4))
+    assert e.update_central_cut((g, ParallelCut(0.0, 0.05))) == CutStatus.Success
+    assert np.array_equal(e.xc(), -0.01 * np.ones(4)) and e.kappa == pytest.approx(0.012, abs=1e-6)
+    e = EllStable.new_with_scalar(0.01, np.zeros(4))
+    assert e.update_bias_cut((g, ParallelCut(0.01, 0.04))) == CutStatus.Success
+    assert e.xc()[0] == pytest.approx(-0.0116, abs=1e-6) and e.kappa == pytest.approx(0.01232, abs=1e-6)
+    e = EllStable.new_with_scalar(0.01, np.zeros(4))
+    assert e.update_q((g, ParallelCut(-0.04, 0.0625))) == CutStatus.NoEffect
+    assert np.array_equal(e.xc(), np.zeros(4)) and e.kappa == 0.01
+
+
+@pytest.mark.parametrize("n,start", [(2, "scalar"), (7, "diag"), (33, "upper"), (64, "upper"), (64, "scalar")])
+def test_ellstable_trajectory_bit_identical(ref, n, start):
+    from ellalgo_rs_b200.ell import EllStable
+    rng = np.random.default_rng(n)
+    xc = rng.uniform(-1, 1, n)
+    kw = dict(kappa=3.0, xc=xc)
+    if start == "diag":
+        kw.update(kappa=1.0, diag=rng.uniform(0.5, 2.0, n))
+    elif start == "upper":
+        kw.update(mq=np.eye(n) + np.triu(rng.uniform(-1e-3, 1e-3, (n, n)), 1))
+    e = EllStable(kw["kappa"], xc, mq=kw.get("mq"), diag=kw.get("diag"))
+    s = ref.Space(A.KIND_ELLSTABLE, n, kappa=kw["kappa"], mq=kw.get("mq"), diag=kw.get("diag"), xc=xc)
+    for k, (which, g, cut) in enumerate(_cuts(n, 9, n + 5)):
+        st_g, st_r = _gpu_update(e, which, g, cut), _ref_update(s, which, g, cut)
+        r = s.state()
+        assert int(st_g) == st_r, f"step {k}: status"
+        assert e.tsq() == r["tsq"] and e.kappa == r["kappa"] and np.array_equal(e.xc(), r["xc"]), f"step {k}"
+    got, want = e.mq, s.state()["mq"]
+    assert np.array_equal(np.triu(got), np.triu(want))      # the factor; the strict lower triangle is scratch in the reference
+    c = e.clone()
+    which, g, cut = _cuts(n, 1, 99)[0]
+    _gpu_update(c, which, g, cut)
+    assert np.array_equal(e.xc(), s.state()["xc"])          # the clone is independent
+
+
+def test_ellstable_driver_quasicvx():  # src/quasicvx.rs:95-105 test_feasible_stable
+    from ellalgo_rs_b200.ell import EllStable
+
+    class Quasicvx:
+        def __init__(self): self.idx = -1
+        def assess_optim(self, xc, gamma):
+            sqrtx, logy = xc
+            for _ in range(2):
+                self.idx = (self.idx + 1) % 2
+                fv = sqrtx * sqrtx - logy if self.idx == 0 else -sqrtx + gamma * math.exp(logy)
+                if fv > 0.0:
+                    g = np.array([2.0 * sqrtx, -1.0]) if self.idx == 0 else np.array([-1.0, gamma * math.exp(logy)])
+                    return (g, SingleCut(fv)), False, gamma
+            return (np.array([-1.0, sqrtx]), SingleCut(0.0)), True, sqrtx / math.exp(logy)
+    x, niter, _ = cutting_plane_optim(Quasicvx(), EllStable.new(np.array([10.0, 10.0]), np.zeros(2)), 0.0, Options(2000, 1e-8))
+    assert x is not None and niter == 49
+    with pytest.raises(Exception):
+        EllStable.new_with_scalar(1.0, np.zeros(65))
