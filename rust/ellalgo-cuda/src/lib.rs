@@ -14,13 +14,16 @@ use ellalgo_rs::arr::Arr;
 use ellalgo_rs::cutting_plane::{CutStatus, ParallelCut, SearchSpace, SingleCut, UpdateByCutChoice};
 use std::ffi::CStr;
 
-pub struct EllCuda {
+/// KIND = 0: `Ell` (src/ell.rs, any n, matrix in HBM); KIND = 1: `EllStable` (src/ell_stable.rs, n <= 64).
+pub struct EllCudaT<const KIND: i32> {
     h: sys::ell_handle,
     n: usize,
 }
+pub type EllCuda = EllCudaT<{ sys::ELL_KIND_ELL }>;
+pub type EllStableCuda = EllCudaT<{ sys::ELL_KIND_ELLSTABLE }>;
 
 // The handle owns device memory and one stream; `&mut self` serialises use exactly like the reference's plain data.
-unsafe impl Send for EllCuda {}
+unsafe impl<const KIND: i32> Send for EllCudaT<KIND> {}
 
 fn check(rc: i32) {
     if rc != sys::ELLCUDA_OK {
@@ -30,11 +33,11 @@ fn check(rc: i32) {
     }
 }
 
-impl EllCuda {
-    fn create(kappa: f64, mq: Option<&Arr>, diag: Option<&Arr>, xc: &Arr) -> EllCuda {
+impl<const KIND: i32> EllCudaT<KIND> {
+    fn create(kappa: f64, mq: Option<&Arr>, diag: Option<&Arr>, xc: &Arr) -> Self {
         let n = xc.len();
         let desc = sys::ell_create_desc {
-            kind: sys::ELL_KIND_ELL,
+            kind: KIND,
             device: 0,
             n: n as i64,
             kappa,
@@ -51,23 +54,23 @@ impl EllCuda {
         };
         let mut h: sys::ell_handle = std::ptr::null_mut();
         check(unsafe { sys::ellcuda_create(&desc, &mut h) });
-        EllCuda { h, n }
+        EllCudaT { h, n }
     }
-    /// src/ell.rs:31-41
-    pub fn new_with_matrix(kappa: f64, mq: Arr, xc: Arr) -> EllCuda {
+    /// src/ell.rs:31-41 / src/ell_stable.rs:18-27
+    pub fn new_with_matrix(kappa: f64, mq: Arr, xc: Arr) -> Self {
         assert_eq!(mq.size(), xc.len() * xc.len());
         Self::create(kappa, Some(&mq), None, &xc)
     }
     /// src/ell.rs:54-56
-    pub fn new(val: Arr, xc: Arr) -> EllCuda {
+    pub fn new(val: Arr, xc: Arr) -> Self {
         Self::create(1.0, None, Some(&val), &xc)
     }
     /// src/ell.rs:65-67
-    pub fn new_with_scalar(val: f64, xc: Arr) -> EllCuda {
+    pub fn new_with_scalar(val: f64, xc: Arr) -> Self {
         Self::create(val, None, None, &xc)
     }
     /// src/ell.rs:76-78
-    pub fn from_covariance(cov: Arr, xc: Arr) -> EllCuda {
+    pub fn from_covariance(cov: Arr, xc: Arr) -> Self {
         Self::new_with_matrix(1.0, cov, xc)
     }
     pub fn kappa(&self) -> f64 {
@@ -93,22 +96,22 @@ impl EllCuda {
     }
 }
 
-impl Clone for EllCuda {
+impl<const KIND: i32> Clone for EllCudaT<KIND> {
     fn clone(&self) -> Self {
         let mut h: sys::ell_handle = std::ptr::null_mut();
         check(unsafe { sys::ellcuda_clone(self.h, &mut h) });
-        EllCuda { h, n: self.n }
+        EllCudaT { h, n: self.n }
     }
 }
 
-impl Drop for EllCuda {
+impl<const KIND: i32> Drop for EllCudaT<KIND> {
     fn drop(&mut self) {
         unsafe { sys::ellcuda_destroy(self.h) }
     }
 }
 
 /// src/ell.rs:140-180
-impl SearchSpace for EllCuda {
+impl<const KIND: i32> SearchSpace for EllCudaT<KIND> {
     type ArrayType = Arr;
     fn xc(&self) -> Arr {
         let mut x = vec![0.0; self.n];
@@ -145,29 +148,29 @@ impl SearchSpace for EllCuda {
 }
 
 /// src/ell.rs:185-196 + :212-229.  The orphan rule allows this impl: the local type is the trait's parameter.
-impl UpdateByCutChoice<EllCuda> for SingleCut {
+impl<const KIND: i32> UpdateByCutChoice<EllCudaT<KIND>> for SingleCut {
     type ArrayType = Arr;
-    fn update_bias_cut_by(&self, e: &mut EllCuda, grad: &Arr) -> CutStatus {
+    fn update_bias_cut_by(&self, e: &mut EllCudaT<KIND>, grad: &Arr) -> CutStatus {
         e.update(sys::ELL_UPDATE_BIAS, grad, self.0, -1, 0.0)
     }
-    fn update_central_cut_by(&self, e: &mut EllCuda, grad: &Arr) -> CutStatus {
+    fn update_central_cut_by(&self, e: &mut EllCudaT<KIND>, grad: &Arr) -> CutStatus {
         e.update(sys::ELL_UPDATE_CENTRAL, grad, self.0, -1, 0.0)
     }
-    fn update_q_by(&self, e: &mut EllCuda, grad: &Arr) -> CutStatus {
+    fn update_q_by(&self, e: &mut EllCudaT<KIND>, grad: &Arr) -> CutStatus {
         e.update(sys::ELL_UPDATE_Q, grad, self.0, -1, 0.0)
     }
 }
 
 /// src/ell.rs:198-210 + :212-229
-impl UpdateByCutChoice<EllCuda> for ParallelCut {
+impl<const KIND: i32> UpdateByCutChoice<EllCudaT<KIND>> for ParallelCut {
     type ArrayType = Arr;
-    fn update_bias_cut_by(&self, e: &mut EllCuda, grad: &Arr) -> CutStatus {
+    fn update_bias_cut_by(&self, e: &mut EllCudaT<KIND>, grad: &Arr) -> CutStatus {
         e.update(sys::ELL_UPDATE_BIAS, grad, self.0, self.1.is_some() as i32, self.1.unwrap_or(0.0))
     }
-    fn update_central_cut_by(&self, e: &mut EllCuda, grad: &Arr) -> CutStatus {
+    fn update_central_cut_by(&self, e: &mut EllCudaT<KIND>, grad: &Arr) -> CutStatus {
         e.update(sys::ELL_UPDATE_CENTRAL, grad, self.0, self.1.is_some() as i32, self.1.unwrap_or(0.0))
     }
-    fn update_q_by(&self, e: &mut EllCuda, grad: &Arr) -> CutStatus {
+    fn update_q_by(&self, e: &mut EllCudaT<KIND>, grad: &Arr) -> CutStatus {
         e.update(sys::ELL_UPDATE_Q, grad, self.0, self.1.is_some() as i32, self.1.unwrap_or(0.0))
     }
 }
