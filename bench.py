@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-large-n", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-1m", action="store_true")
     ap.add_argument("--per-gpu", type=int, default=PER_GPU)
     ap.add_argument("--large-n", type=int, default=LARGE_N)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
@@ -269,6 +270,33 @@ def main():
     e2e_iters = sum_over_ranks(float(iterations_done(hres_t["num_iters"].numpy(), hres_t["exit_status"].numpy()))) * args.steps
     e2e_value = e2e_iters / t_e2e
     clocks = sampler.stop() if sampler else None
+
+    # ---------------------------------------------------------------- north_star's own target shape: 2^20 n=32 problems / GPU
+    extra_1m = None
+    if not args.skip_1m:
+        c1 = 1 << 20
+        hb = W.bowl(c1, n=N_TAPS, first=rank * c1, max_iters=2000)     # SURVEY C3': cap 2000 -> every problem runs 2000 iterations
+        db = BatchProblem(oracle_id=A.ORACLE_BOWL, n=N_TAPS, count=c1, kappa0=torch.from_numpy(hb.kappa0).to(dev),
+                          xc0=torch.from_numpy(hb.xc0).to(dev), gamma0=torch.from_numpy(hb.gamma0).to(dev),
+                          params=torch.from_numpy(hb.params).to(dev), max_iters=2000, tolerance=hb.tolerance, device=local)
+        rb = {"num_iters": torch.zeros(c1, dtype=torch.int64, device=dev), "exit_status": torch.zeros(c1, dtype=torch.int32, device=dev),
+              "xbest": torch.zeros(c1, N_TAPS, dtype=torch.float64, device=dev), "has_xbest": torch.zeros(c1, dtype=torch.uint8, device=dev),
+              "gamma": torch.zeros(c1, dtype=torch.float64, device=dev)}
+        batch.solve_batch_device(db, rb, sptr)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        batch.solve_batch_device(db, rb, sptr)
+        b1.record(stream)
+        barrier()
+        tb = max_over_ranks(b0.elapsed_time(b1) / 1e3)
+        itb = sum_over_ranks(float(iterations_done(rb["num_iters"].cpu().numpy(), rb["exit_status"].cpu().numpy())))
+        extra_1m = {"workload": "SURVEY C3': 2^20 quadratic-bowl problems per GPU, n=32, Ell::new_with_scalar(100,0), max_iters capped at 2000",
+                    "value": itb / tb, "unit": "iterations/s", "ms": 1e3 * tb,
+                    "equivalent_streaming_GBs_per_gpu": itb / tb / world * 16.0 * N_TAPS * N_TAPS / 1e9,
+                    "frac_of_nominal_8TBs": itb / tb / world * 16.0 * N_TAPS * N_TAPS / 8e12,
+                    "target": "north_star: >= 50 % of the HBM roofline = 2.44e8 iterations/s per GPU"}
+        del db, rb
 
     # ---------------------------------------------------------------- large n (second half of the metric)
     large = None
@@ -406,6 +434,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
+            "bowl_1m": extra_1m,
             "large_n": large,
         }
         print(json.dumps(line), flush=True)
