@@ -340,14 +340,14 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     }
 }
 
-// returns false on timeout (~2 s) so that a lost peer cannot hang the GPU
+// returns false on timeout (~10 s) so that a lost peer cannot hang the GPU
 __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long epoch) {
     const long long t0 = clock64();
     for (;;) {
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
         if (v >= epoch) return true;
-        if (clock64() - t0 > 4000000000LL) return false;
+        if (clock64() - t0 > 20000000000LL) return false;
         __nanosleep(100);
     }
 }
