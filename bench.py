@@ -362,7 +362,11 @@ def main():
                          "achieved": slab_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": slab_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": slab_bytes / (sweep_ms * 1e-3) / 1e9 / 8000.0,
-                         "ms_per_launch": sweep_ms, "algorithmic_bytes_per_launch": slab_bytes, "traffic": None,
+                         "ms_per_launch": sweep_ms, "algorithmic_bytes_per_launch": slab_bytes,
+                         # ncu --set full of this very launch shape (n=16384, whole matrix): dram__bytes_read.sum 2.148194e9 +
+                         # dram__bytes_write.sum 2.089145e9 (profiles/r01b_prof_sweep2_raw.csv); not re-measured per run
+                         "traffic": 4237339000.0 if (world == 1 and n == 16384) else None,
+                         "traffic_source": "profiles/r01b_prof_sweep2_raw.csv" if (world == 1 and n == 16384) else None,
                          "timing": "median of 60 CUDA-event pairs around the sweep launches of an eager run (phase B)"},
         }
         del ell
@@ -425,7 +429,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "batch_warp_kernel<OrLowpass> (persistent, one warp per problem)",
                          "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                         "ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes, "traffic": None,
+                         "ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         # real DRAM traffic is inputs + results only: ncu (4736-problem launch, profiles/r01b_prof_batch2_raw.csv)
+                         # read 0.45 MB, wrote < 1 MB — scaled by problem count here, not re-measured per run
+                         "traffic": float(h2d + d2h),
                          "note": "equivalent-streaming figure of SURVEY.md 8d: 16*n^2 bytes per iteration (M read once, written "
                                  "once) although M never leaves the register file; see large_n.roofline for the kernel that "
                                  "really streams HBM"},
