@@ -73,7 +73,7 @@ struct OrBowl {  // tests/integration_test.rs:90-105
     static constexpr bool kNeedsTable = false;
 };
 
-template <bool FIXED32, int kRowsPerLane>
+template <bool FIXED32, int kRowsPerLane, bool XREG = false>
 struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
     int idx1, idx2, idx3, nwpass, nwstop, mdim, kmax;
     double lp_sq, up_sq, sp_sq, fmax;
@@ -92,14 +92,20 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
     // spectrum[k].dot(x) for the R rows this lane evaluates in one round: each sum is sequential over j
     // (src/arr.rs:443-451); x is the broadcast copy in c.sx(); the R chains are independent and interleave.
     template <int R>
-    __device__ __forceinline__ void row_dots(const WarpCtx& c, const int (&k)[R], double (&acc)[R]) const {
+    __device__ __forceinline__ void row_dots(const WarpCtx& c, const int (&k)[R], double (&acc)[R], const double (&xr)[32]) const {
         const double* row[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             row[r] = c.tab + (long long)k[r] * c.tab_stride;
             acc[r] = 0.0;
         }
-        if constexpr (FIXED32) {
+        if constexpr (FIXED32 && XREG) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] += row[r][j] * xr[j];
+            }
+        } else if constexpr (FIXED32) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 const double2 x = *reinterpret_cast<const double2*>(c.sx() + j);
@@ -124,7 +130,7 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
     // at the first row in traversal order that violates.  BAND: 0 pass-band (:62-78), 1 stop-band (:83-104),
     // 2 transition band (:106-119).  Returns true when a cut was produced.
     template <int BAND, int R>
-    __device__ __forceinline__ bool sweep(const WarpCtx& c, int lo, int hi, int& cursor, double& g, Cut& cut) {
+    __device__ __forceinline__ bool sweep(const WarpCtx& c, int lo, int hi, int& cursor, double& g, Cut& cut, const double (&xr)[32]) {
         const int len = hi - lo;
         double best_v = -INFINITY;
         int best_c = 0x7fffffff, best_k = -1;
@@ -138,7 +144,7 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
                 if (kk >= hi) kk -= len;
                 k[r] = cidx < len ? kk : lo;      // inactive slots read a valid row and are masked below
             }
-            row_dots<R>(c, k, val);
+            row_dots<R>(c, k, val, xr);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int cidx = base + 32 * r + c.lane;
@@ -192,10 +198,18 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
     __device__ bool assess_optim(const WarpCtx& c, double xc, double& gamma, double& g, Cut& cut) {  // :137-150
         (void)xc;
         sp_sq = gamma;
-        if (sweep<0, kRowsPerLane>(c, 0, nwpass, idx1, g, cut)) return false;
+        double xr[32];
+        if constexpr (FIXED32 && XREG) {   // x once per oracle call instead of once per round
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(c.sx() + j);
+                xr[j] = v.x; xr[j + 1] = v.y;
+            }
+        }
+        if (sweep<0, kRowsPerLane>(c, 0, nwpass, idx1, g, cut, xr)) return false;
         fmax = -INFINITY; kmax = -1;
-        if (sweep<1, kRowsPerLane>(c, nwstop, mdim, idx3, g, cut)) return false;
-        if (sweep<2, kRowsPerLane>(c, nwpass, nwstop, idx2, g, cut)) return false;
+        if (sweep<1, kRowsPerLane>(c, nwstop, mdim, idx3, g, cut, xr)) return false;
+        if (sweep<2, kRowsPerLane>(c, nwpass, nwstop, idx2, g, cut, xr)) return false;
         const double x0 = c.sx()[0];
         if (x0 < 0.0) {  // :123-127
             g = c.lane == 0 ? -1.0 : 0.0;
@@ -421,7 +435,8 @@ int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_
         if (a.n != 32) rc = launch_one<OrLowpass<false, 1>, false, 8, 1>(a, s, sm_count);
         else if (v == 1) rc = launch_one<OrLowpass<true, 2>, true, 8, 1>(a, s, sm_count);
         else if (v == 2) rc = launch_one<OrLowpass<true, 1>, true, 16, 1>(a, s, sm_count);
-        else rc = launch_one<OrLowpass<true, 1>, true, 8, 1>(a, s, sm_count);
+        else if (v == 3) rc = launch_one<OrLowpass<true, 1, false>, true, 8, 1>(a, s, sm_count);   // x re-read per round: 404
+        else rc = launch_one<OrLowpass<true, 1, true>, true, 8, 1>(a, s, sm_count);   // x held across the band sweeps: 413 M iter/s
     } else {
         set_error("oracle not available in the warp-per-problem kernel");
         return ELLCUDA_E_ARG;
