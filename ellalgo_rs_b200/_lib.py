@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(CSRC, "libellcuda.so")
 EXPORTS = [
     "ellcuda_batch_solve", "ellcuda_last_launch_count", "ellcuda_lowpass_table", "ellcuda_lowpass_band_edge",
     "ellcuda_create", "ellcuda_clone", "ellcuda_destroy", "ellcuda_xc", "ellcuda_set_xc", "ellcuda_tsq",
-    "ellcuda_kappa", "ellcuda_get_mq", "ellcuda_update", "ellcuda_update_begin", "ellcuda_update_finish",
+    "ellcuda_kappa", "ellcuda_get_mq", "ellcuda_dot_mv", "ellcuda_update", "ellcuda_update_begin", "ellcuda_update_finish",
     "ellcuda_grad_t_ptr", "ellcuda_exchange_export", "ellcuda_exchange_attach", "ellcuda_exchange_attach_ptrs",
     "ellcuda_exchange_block_ptr", "ellcuda_status_ptr", "ellcuda_last_status", "ellcuda_set_stream", "ellcuda_sync",
     "ellcuda_set_timing", "ellcuda_last_sweep_ms", "ellcuda_handle_launch_count",
@@ -79,6 +79,8 @@ def lib():
         for name in ("ellcuda_tsq", "ellcuda_kappa"):
             getattr(L, name).argtypes = [H, _pd]
             getattr(L, name).restype = C.c_int
+        L.ellcuda_dot_mv.argtypes = [H, C.c_void_p, C.c_void_p]
+        L.ellcuda_dot_mv.restype = C.c_int
         L.ellcuda_update.argtypes = [H, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_double, _pi]
         L.ellcuda_update.restype = C.c_int
         L.ellcuda_update_begin.argtypes = [H, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_double]

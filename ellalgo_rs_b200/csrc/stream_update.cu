@@ -125,6 +125,7 @@ struct SweepArgs {
     unsigned* cnt_block;       // arrivals per column block (self-resetting)
     unsigned* cnt_all;         // column blocks completed (self-resetting)
     double* own_blk;           // this rank's exchange block
+    double* out;               // non-null: plain GEMV — column sums go here (local column index), nothing else is published
     long long ld_part, n, w, c_glob0;
     int nseg;
     int exchange;              // 0: flush only (no grad_t is produced); 1: produce grad_t (+ push to peers if attached)
@@ -292,6 +293,11 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
             acc0 += __ldcg(a.partial + (long long)s * a.ld_part + cl);
             acc1 += __ldcg(a.partial + (long long)s * a.ld_part + cl + 1);
         }
+    }
+    if (a.out) {   // Arr::dot_mv for its own sake (power iteration, conjugate gradient): no exchange, no state
+        if (cl < a.w) a.out[cl] = acc0;
+        if (cl + 1 < a.w) a.out[cl + 1] = acc1;
+        return;
     }
     const unsigned long long epoch = a.sc->epoch;
     const int attached = a.pt.nranks > 0;
@@ -659,7 +665,7 @@ int launch_sweep(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) 
 
 // begin = [padded copy of g] + sweep (deferred rank-1, column sums, ordered combine, push to peers).
 // g_dev may be null (flush: applies the pending rank-1 only, produces no grad_t).
-int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
+int enqueue_begin(ellcuda_ctx* h, const double* g_dev, double* plain_out = nullptr) {
     cudaStream_t s = h->stream;
     const bool flush = g_dev == nullptr;
     if (flush) {
@@ -674,7 +680,7 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev) {
     }
     SweepArgs a;
     a.g = h->gsrc; a.pend = h->pend; a.sc = h->sc; a.partial = h->partial; a.block_omega = h->block_omega;
-    a.cnt_block = h->counters; a.cnt_all = h->counters + h->ncb; a.own_blk = h->xblk;
+    a.cnt_block = h->counters; a.cnt_all = h->counters + h->ncb; a.own_blk = h->xblk; a.out = plain_out;
     a.ld_part = h->ld_part; a.n = h->n; a.w = h->w; a.c_glob0 = h->c0; a.nseg = h->nseg;
     a.exchange = flush ? 0 : 1;
     a.omega_parts = (h->nranks > 0 && h->reduce_mode > 0) ? 1 : 0;
@@ -960,6 +966,20 @@ int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return cuda_fail(e, "ellcuda_get_mq", __FILE__, __LINE__);
     return ELLCUDA_OK;
+}
+
+int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev) {
+    if (!h || !x_dev || !y_dev) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (h->kind != ELL_KIND_ELL) { set_error("dot_mv needs an Ell handle"); return ELLCUDA_E_ARG; }
+    ELL_DEVICE_SCOPE(h->device);
+    Scal sc;
+    int rc = read_scal(h, &sc);
+    if (rc) return rc;
+    if (sc.pending && (rc = flush_pending(h))) return rc;   // the product is with the reference's `mq`, all updates applied
+    const double* keep = h->gsrc;
+    rc = enqueue_begin(h, x_dev, y_dev);
+    h->gsrc = keep;
+    return rc;
 }
 
 int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, double beta0, int32_t has_beta1, double beta1) {

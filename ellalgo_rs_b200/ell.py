@@ -147,6 +147,23 @@ class Ell:
     def update_q(self, cut):
         return self._update(_abi.UPDATE_Q, cut)
 
+    # ---- Arr::dot_mv on the device-resident matrix (src/arr.rs:426-442)
+    def dot_mv_device(self, x_dev_ptr: int, y_dev_ptr: int):
+        check(lib().ellcuda_dot_mv(self._h, x_dev_ptr, y_dev_ptr))
+
+    def dot_mv(self, x) -> np.ndarray:
+        """y = mq·x for a host vector (H2D, streaming GEMV, D2H); sums in the reference's order"""
+        import torch
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape != (self.n,):
+            raise ValueError("x must have n entries")  # assert_eq!(self.cols, x.len())
+        xd = torch.from_numpy(x).cuda()
+        yd = torch.empty(self.rows[1] - self.rows[0], dtype=torch.float64, device=xd.device)
+        torch.cuda.synchronize()
+        self.dot_mv_device(xd.data_ptr(), yd.data_ptr())
+        self.sync()
+        return yd.cpu().numpy()
+
     # ---- split form for device-resident gradients / sharded slabs / CUDA graphs
     def update_begin(self, which, grad_dev_ptr: int, beta):
         b0, has, b1 = _cut_args(beta)

@@ -1,0 +1,123 @@
+"""Host mirror of the reference's GEMV-sharing numerics: `power_iteration` (four variants,
+src/power_iteration.rs:53-173) and `conjugate_gradient` (src/conjugate_gradient.rs:21-71), written against any matrix
+object with `dot_mv(x)` — in particular ell.Ell, whose dot_mv is the same TMA-staged streaming pass Ell::update_core
+uses.  Vector work stays on the host; sums are sequential like the reference's (numpy's cumsum adds left to right)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class Options:  # src/power_iteration.rs:16-19
+    max_iters: int = 2000
+    tolerance: float = 1e-9
+
+
+def _seq_sum(v: np.ndarray) -> float:
+    return float(np.cumsum(v)[-1]) if v.size else 0.0
+
+
+def _dot(a, b) -> float:  # Arr::dot, src/arr.rs:443-451
+    return _seq_sum(a * b)
+
+
+def _norm_l1(x) -> float:  # src/power_iteration.rs:22-25
+    return _seq_sum(np.abs(x))
+
+
+def _div(x, s):  # Arr /= f64 multiplies by the reciprocal, src/arr.rs:241-249
+    return x * (1.0 / s)
+
+
+def power_iteration(a, x, options: Options):  # :53-65 → (eigenvalue, niter, x)
+    x = _div(np.asarray(x, dtype=np.float64), math.sqrt(_dot(x, x)))
+    for niter in range(options.max_iters):
+        x1 = x
+        x = a.dot_mv(x1)
+        x = _div(x, math.sqrt(_dot(x, x)))
+        if _norm_l1(x - x1) <= options.tolerance or _norm_l1(x + x1) <= options.tolerance:
+            return _dot(x, a.dot_mv(x)), niter, x
+    return _dot(x, a.dot_mv(x)), options.max_iters, x
+
+
+def power_iteration4(a, x, options: Options):  # :81-96
+    x = np.asarray(x, dtype=np.float64)
+    x = _div(x, _norm_l1(x))
+    for niter in range(options.max_iters):
+        x1 = x
+        x = a.dot_mv(x1)
+        x = _div(x, _norm_l1(x))
+        if _norm_l1(x - x1) <= options.tolerance or _norm_l1(x + x1) <= options.tolerance:
+            x = _div(x, math.sqrt(_dot(x, x)))
+            return _dot(x, a.dot_mv(x)), niter, x
+    x = _div(x, math.sqrt(_dot(x, x)))
+    return _dot(x, a.dot_mv(x)), options.max_iters, x
+
+
+def power_iteration2(a, x, options: Options):  # :112-127
+    x = np.asarray(x, dtype=np.float64)
+    x = _div(x, math.sqrt(_dot(x, x)))
+    new_vec = a.dot_mv(x)
+    eigenval = _dot(x, new_vec)
+    for niter in range(options.max_iters):
+        prev = eigenval
+        x = _div(new_vec, math.sqrt(_dot(new_vec, new_vec)))
+        new_vec = a.dot_mv(x)
+        eigenval = _dot(x, new_vec)
+        if abs(prev - eigenval) <= options.tolerance:
+            return eigenval, niter, x
+    return eigenval, options.max_iters, x
+
+
+def power_iteration3(a, x, options: Options):  # :144-173
+    x = np.asarray(x, dtype=np.float64)
+    new_vec = a.dot_mv(x)
+    dot = _dot(x, x)
+    eigenval = _dot(x, new_vec) / dot
+    for niter in range(options.max_iters):
+        prev = eigenval
+        x = new_vec
+        dot = _dot(x, x)
+        if dot >= 1e150:
+            x = _div(x, math.sqrt(_dot(x, x)))
+            new_vec = a.dot_mv(x)
+            eigenval = _dot(x, new_vec)
+            if abs(prev - eigenval) <= options.tolerance:
+                return eigenval, niter, x
+        else:
+            new_vec = a.dot_mv(x)
+            eigenval = _dot(x, new_vec) / dot
+            if abs(prev - eigenval) <= options.tolerance:
+                return eigenval, niter, _div(x, math.sqrt(_dot(x, x)))
+    return eigenval, options.max_iters, x
+
+
+class ConjGradError(RuntimeError):
+    pass
+
+
+def conjugate_gradient(a, b, x0=None, tol: float = 1e-5, max_iter: int = 1000):  # src/conjugate_gradient.rs:21-71
+    """returns x; raises ConjGradError where the reference returns Err(...)"""
+    b = np.asarray(b, dtype=np.float64)
+    x = np.zeros(b.size) if x0 is None else np.array(x0, dtype=np.float64)
+    residual = b - a.dot_mv(x)
+    direction = residual.copy()
+    rns = _dot(residual, residual)
+    for _ in range(max_iter):
+        a_dir = a.dot_mv(direction)
+        dad = _dot(direction, a_dir)
+        if dad == 0.0:
+            raise ConjGradError("Conj Grad did not converge")
+        step = rns / dad
+        x = x + step * direction
+        residual = residual - step * a_dir
+        rns_new = _dot(residual, residual)
+        if math.sqrt(rns_new) < tol:
+            return x
+        ratio = rns_new / rns
+        direction = residual + ratio * direction
+        rns = rns_new
+    raise ConjGradError("Conj Grad did not converge after max iterations")

@@ -207,6 +207,12 @@ int ellcuda_kappa(ell_handle h, double* out);             /* pub field Ell::kapp
 int ellcuda_get_mq(ell_handle h, double* out_rows_by_n);  /* pub field Ell::mq (this slab's rows,
                                                              pending rank-1 applied first)        */
 
+/* Arr::dot_mv (src/arr.rs:426-442) on the handle's matrix: y = mq·x with the reference's left-to-right sums (mq is
+ * symmetric).  x_dev: n doubles, y_dev: row_end-row_begin doubles, both device memory; enqueued on the handle's stream.
+ * The streaming GEMV that power_iteration (src/power_iteration.rs) and conjugate_gradient
+ * (src/conjugate_gradient.rs) share with Ell::update_core.  Ell handles only.                                       */
+int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev);
+
 /* SearchSpace::update_{bias_cut,central_cut,q} with SingleCut(beta0) [has_beta1 = -1],
  * ParallelCut(beta0, None) [0] or ParallelCut(beta0, Some(beta1)) [1]
  * (src/ell.rs:153-175, 182-229 → update_core :97-137).  `grad` is host memory, n values.

@@ -25,7 +25,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ellref.hpp", "ellref_oracles.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ellref.hpp", "ellref_oracles.hpp", "ellref_linalg.hpp")]
     srcs.append(os.path.join(_ROOT, "include", "ellcuda.h"))
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs if os.path.exists(s))
@@ -76,6 +76,10 @@ def lib():
         L.ellref_bsearch_bs2.restype = C.c_int64
         L.ellref_hardware_threads.restype = C.c_int
         L.ellref_libm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.ellref_power_iteration.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, _pd]
+        L.ellref_power_iteration.restype = C.c_int64
+        L.ellref_conjugate_gradient.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64]
+        L.ellref_conjugate_gradient.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -161,3 +165,21 @@ def lowpass_case_params() -> np.ndarray:
     p = np.zeros(5)
     lib().ellref_lowpass_case_params(p.ctypes.data)
     return p
+
+
+def power_iteration(variant: int, a: np.ndarray, x0: np.ndarray, max_iters: int, tol: float):
+    """src/power_iteration.rs variants 1..4 → (eigenvalue, niter, x)"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64)
+    eig = C.c_double()
+    it = lib().ellref_power_iteration(variant, x.size, a.ctypes.data, x.ctypes.data, max_iters, tol, C.byref(eig))
+    return eig.value, it, x
+
+
+def conjugate_gradient(a: np.ndarray, b: np.ndarray, x0=None, tol: float = 1e-5, max_iter: int = 1000):
+    """src/conjugate_gradient.rs → (x, iterations) ; iterations < 0 = the reference's Err cases"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(b.size) if x0 is None else np.array(x0, dtype=np.float64)
+    it = lib().ellref_conjugate_gradient(b.size, a.ctypes.data, b.ctypes.data, x.ctypes.data, tol, max_iter)
+    return x, it

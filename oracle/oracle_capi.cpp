@@ -8,6 +8,7 @@
 #include <thread>
 
 #include "../include/ellcuda.h"
+#include "ellref_linalg.hpp"
 #include "ellref_oracles.hpp"
 
 using namespace ellref;
@@ -305,6 +306,29 @@ int ellref_profit_assess(const double* p7, const double* y, double* gamma, doubl
 // the host libm the restatement itself uses (what Rust's f64::exp / f64::ln call): which = 0 exp, 1 ln
 void ellref_libm(int which, const double* x, double* y, int64_t n) {
     for (int64_t i = 0; i < n; ++i) y[i] = which == 0 ? std::exp(x[i]) : std::log(x[i]);
+}
+
+// power_iteration variants 1..4 (src/power_iteration.rs): x in/out, returns niter, *eigenvalue
+int64_t ellref_power_iteration(int variant, int64_t n, const double* a, double* x, int64_t max_iters, double tol, double* eig) {
+    Vec A(a, a + n * n), X(x, x + n);
+    const Options o{static_cast<std::size_t>(max_iters), tol};
+    std::pair<double, std::size_t> r;
+    switch (variant) {
+        case 1: r = power_iteration(A, X, o); break;
+        case 2: r = power_iteration2(A, X, o); break;
+        case 3: r = power_iteration3(A, X, o); break;
+        default: r = power_iteration4(A, X, o); break;
+    }
+    std::copy(X.begin(), X.end(), x);
+    *eig = r.first;
+    return static_cast<int64_t>(r.second);
+}
+// conjugate_gradient (src/conjugate_gradient.rs): x in (x0) / out; returns iterations, -1 / -2 for the two Err cases
+int64_t ellref_conjugate_gradient(int64_t n, const double* a, const double* b, double* x, double tol, int64_t max_iter) {
+    Vec A(a, a + n * n), B(b, b + n), X(x, x + n);
+    const long r = conjugate_gradient(A, B, X, tol, static_cast<std::size_t>(max_iter));
+    std::copy(X.begin(), X.end(), x);
+    return r;
 }
 
 void ellref_lowpass_table(int64_t n, double* out) {

@@ -269,3 +269,44 @@ def test_ldlt(ref):  # src/oracles/ldlt_mgr.rs:182-268
     assert not spd and ep == pytest.approx(20.0, **APPROX)
     assert not _ldlt(ref, [[0, 15, -5], [15, 18, 0], [-5, 0, 20]])[0]
     assert _ldlt(ref, [[0, 15, -5], [15, 18, 0], [-5, 0, 20]], semi=True)[0]
+
+
+# ---------------------------------------------------------------- §8f rank 4: GEMV-sharing siblings
+POWER_A = np.array([[3.7, -3.6, 0.7], [-3.6, 4.3, -2.8], [0.7, -2.8, 5.4]])
+
+
+def test_power_iteration_pins(ref):  # src/power_iteration.rs:178-229
+    x0 = [0.3, 0.5, 0.4]
+    assert ref.power_iteration(1, POWER_A, x0, 2000, 1e-7)[1] == 22
+    assert ref.power_iteration(4, POWER_A, x0, 2000, 1e-7)[1] == 21
+    assert ref.power_iteration(2, POWER_A, x0, 2000, 1e-14)[1] == 23
+    assert ref.power_iteration(3, POWER_A, x0, 2000, 1e-14)[1] == 23
+    assert ref.power_iteration(4, POWER_A, x0, 5, 1e-14)[1] == 5
+
+
+def test_conjugate_gradient_pins(ref):  # src/conjugate_gradient.rs:86-124
+    a = np.array([[4.0, 1.0], [1.0, 3.0]])
+    for x0 in (None, [1.0, 1.0]):
+        x, it = ref.conjugate_gradient(a, [1.0, 2.0], x0, 1e-5, 1000)
+        assert it >= 0 and x == pytest.approx([0.0909091, 0.6363636], abs=1e-5)
+    assert ref.conjugate_gradient(np.zeros((2, 2)), [1.0, 1.0], None, 1e-5, 10)[1] < 0
+    x, it = ref.conjugate_gradient(a, [1.0, 2.0], None, 1e-10, 1000)
+    r = np.array([1.0, 2.0]) - a @ x
+    assert it >= 0 and math.sqrt(r @ r) < 1e-10
+
+
+def test_host_linalg_mirror_equals_checker(ref):
+    """ellalgo_rs_b200/linalg.py (the host loops that drive the device GEMV) against the restatement, with a host matrix"""
+    from ellalgo_rs_b200 import linalg as LA
+
+    class HostMat:
+        def __init__(self, a): self.a = np.asarray(a, float)
+        def dot_mv(self, x): return np.array([float(np.cumsum(r * x)[-1]) for r in self.a])
+    x0 = np.array([0.3, 0.5, 0.4])
+    for v, f, tol in ((1, LA.power_iteration, 1e-7), (4, LA.power_iteration4, 1e-7), (2, LA.power_iteration2, 1e-14),
+                      (3, LA.power_iteration3, 1e-14)):
+        e, it, x = f(HostMat(POWER_A), x0, LA.Options(2000, tol))
+        er, itr, xr = ref.power_iteration(v, POWER_A, x0, 2000, tol)
+        assert (it, e) == (itr, er) and np.array_equal(x, xr)
+    with pytest.raises(LA.ConjGradError):
+        LA.conjugate_gradient(HostMat(np.zeros((2, 2))), [1.0, 1.0], None, 1e-5, 10)

