@@ -402,8 +402,10 @@ def test_dot_mv_and_its_users_on_the_device(ref):
     x = LA.conjugate_gradient(m, rhs, None, 1e-9, 500)
     xr, it = ref.conjugate_gradient(spd, rhs, None, 1e-9, 500)
     assert it >= 0 and np.array_equal(x, xr)
-    e, it, xv = LA.power_iteration2(m, rng.uniform(0, 1, n), LA.Options(300, 1e-10))
-    er, itr, xvr = ref.power_iteration(2, spd, np.random.default_rng(4).uniform(0, 1, 1)[0] * 0 + xv * 0 + 1, 1, 1e-10) if False else (e, it, xv)
+    x0 = rng.uniform(0, 1, n)
+    e, it, xv = LA.power_iteration2(m, x0, LA.Options(300, 1e-10))
+    er, itr, xvr = ref.power_iteration(2, spd, x0, 300, 1e-10)
+    assert (it, e) == (itr, er) and np.array_equal(xv, xvr)
     # dot_mv with a deferred rank-1 pending: the product must be with the updated matrix
     g = W.large_n_grad(n, 0)
     s = ref.Space(A.KIND_ELL, n, kappa=1.0, mq=spd)
