@@ -51,7 +51,10 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise EllCudaError(_abi.E_CUDA, f"{LIB_PATH} is missing — run __graft_entry__.build(); there is no CPU fallback")
+        try:                      # a fresh checkout: compile once (nvcc is part of the image); never a CPU substitute
+            build()
+        except Exception as exc:
+            raise EllCudaError(_abi.E_CUDA, f"{LIB_PATH} is missing and could not be built ({exc}); there is no CPU fallback")
     L = C.CDLL(LIB_PATH)
     L.ellcuda_batch_solve.argtypes = [C.POINTER(_abi.BatchDesc), C.POINTER(_abi.BatchResult)]
     L.ellcuda_batch_solve.restype = C.c_int
