@@ -34,11 +34,12 @@
 namespace ellcuda {
 namespace {
 
-constexpr int kCols = 64;    // columns per warp (2 per lane)
+constexpr int kColsMax = 64;  // columns per warp: 64 (2 per lane), 32 (1 per lane) or 16 (lanes 0..15) — narrower blocks give
+                              // bit-identical mode enough warps at medium n (n/COLS column blocks)
 constexpr int kRowsDefault = 64;    // rows per TMA tile   (measured at n=16384: 64x3 682 us, 32x6 693, 48x4 692,
 constexpr int kStagesDefault = 3;   // smem ring depth      32x4 709, 48x3 753, 32x3 840, 16x8 831, 64x4 1219 [1 CTA/SM])
 constexpr int kRowsMax = 64;
-// per tile: kCols*ROWS*8 bytes of M, ROWS*8 bytes of g and ROWS*16 bytes of {gt[i], ratio*gt[i]}
+// per tile: COLS*ROWS*8 bytes of M, ROWS*8 bytes of g and ROWS*16 bytes of {gt[i], ratio*gt[i]}
 
 struct Scal {  // device-resident scalars of the Ell (src/ell.rs:9-16) + the deferred rank-1
     double kappa;
@@ -142,42 +143,47 @@ __global__ void copy_pad_kernel(const double* __restrict__ g_in, double* __restr
 // MODE 0: every row of the tile is above the block's columns (i < c):   update = (ratio·gt[c]) · gt[i]
 // MODE 1: every row is at or below them (i >= c):                        update = (ratio·gt[i]) · gt[c]
 // MODE 2: the tile crosses the diagonal: choose per element.             (src/ell.rs:118-127: hi = max, lo = min)
-template <int MODE, bool PENDING, bool SCALE>
-__device__ __forceinline__ void tile_rows(double2* __restrict__ tile, const double* __restrict__ gs, const double2* __restrict__ pd,
+template <int COLS, int MODE, bool PENDING, bool SCALE>
+__device__ __forceinline__ void tile_rows(double* __restrict__ tile_raw, const double* __restrict__ gs, const double2* __restrict__ pd,
                                           int lane, int nrows, int row0, int col0, double gt_c0, double gt_c1, double rg_c0,
                                           double rg_c1, double scale, double& acc0, double& acc1) {
+    constexpr bool TWO = COLS == 64;                     // two columns per lane (16-byte accesses) or one
+    if (COLS < 32 && lane >= COLS) return;               // 16-column blocks: the upper half-warp has no column
 #pragma unroll 8
     for (int r = 0; r < nrows; ++r) {  // nrows < tile height only in the last tile of a segment (rows past n are not M)
-        double2 m = tile[r * (kCols / 2) + lane];
+        double2 m;
+        if (TWO) m = reinterpret_cast<double2*>(tile_raw)[r * (COLS / 2) + lane];
+        else { m.x = tile_raw[r * COLS + lane]; m.y = 0.0; }
         const double gi = gs[r];       // broadcast
         if (PENDING) {
             const double2 p = pd[r];   // broadcast: {gt[i], ratio*gt[i]}
-            double u0, u1;
+            double u0, u1 = 0.0;
             if (MODE == 0) {
                 u0 = rg_c0 * p.x;
-                u1 = rg_c1 * p.x;
+                if (TWO) u1 = rg_c1 * p.x;
             } else if (MODE == 1) {
                 u0 = p.y * gt_c0;
-                u1 = p.y * gt_c1;
+                if (TWO) u1 = p.y * gt_c1;
             } else {
                 const int i = row0 + r;
                 u0 = (i >= col0) ? p.y * gt_c0 : rg_c0 * p.x;
-                u1 = (i >= col0 + 1) ? p.y * gt_c1 : rg_c1 * p.x;
+                if (TWO) u1 = (i >= col0 + 1) ? p.y * gt_c1 : rg_c1 * p.x;
             }
             m.x -= u0;
-            m.y -= u1;
+            if (TWO) m.y -= u1;
             if (SCALE) {
                 m.x *= scale;  // mq *= kappa   (src/ell.rs:132-135)
-                m.y *= scale;
+                if (TWO) m.y *= scale;
             }
-            tile[r * (kCols / 2) + lane] = m;
+            if (TWO) reinterpret_cast<double2*>(tile_raw)[r * (COLS / 2) + lane] = m;
+            else tile_raw[r * COLS + lane] = m.x;
         }
         acc0 += m.x * gi;  // grad_t[c] += M[i][c] * g[i], i ascending
-        acc1 += m.y * gi;
+        if (TWO) acc1 += m.y * gi;
     }
 }
 
-template <int kRows, int kStages, bool PENDING, bool SCALE>
+template <int kCols, int kRows, int kStages, bool PENDING, bool SCALE>
 __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepArgs& a, long long row_lo, long long row_hi, double scale,
                                            unsigned char* smem_raw, double& acc0, double& acc1) {
     constexpr int kTileBytes = kCols * kRows * 8;
@@ -211,8 +217,9 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
         for (int t = 0; t < pre; ++t) issue(t);
     }
 
-    // this lane's two columns (global indices) and their entries of the deferred rank-1 vectors
-    const long long cg0 = a.c_glob0 + c_loc0 + 2 * lane;
+    // this lane's column(s) (global indices) and their entries of the deferred rank-1 vectors
+    constexpr int kPerLane = kCols == 64 ? 2 : 1;
+    const long long cg0 = a.c_glob0 + c_loc0 + kPerLane * (kCols < 32 ? (lane % kCols) : lane);
     double gt_c0 = 0.0, gt_c1 = 0.0, rg_c0 = 0.0, rg_c1 = 0.0;
     if (PENDING) {
         const double2 p0 = a.pend[cg0], p1 = a.pend[cg0 + 1];  // pend is padded, always readable
@@ -224,17 +231,17 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % kStages;
         mbar_wait(&bars[s], (unsigned)((t / kStages) & 1));
-        double2* tile = reinterpret_cast<double2*>(tiles + s * kTileBytes);
+        double* tile = reinterpret_cast<double*>(tiles + s * kTileBytes);
         const double2* pd = reinterpret_cast<const double2*>(pends + s * kPendBytes);
         const double* gs = reinterpret_cast<const double*>(gss + s * kGBytes);
         const long long r0 = row_lo + (long long)t * kRows;
         const int nrows = (int)((row_hi - r0) < kRows ? (row_hi - r0) : kRows);
         if (r0 + kRows <= blk_lo)
-            tile_rows<0, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
+            tile_rows<kCols, 0, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
         else if (r0 >= blk_hi - 1)
-            tile_rows<1, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
+            tile_rows<kCols, 1, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
         else
-            tile_rows<2, PENDING, SCALE>(tile, gs, pd, lane, nrows, (int)(r0 - blk_lo), 2 * lane, gt_c0, gt_c1, rg_c0, rg_c1,
+            tile_rows<kCols, 2, PENDING, SCALE>(tile, gs, pd, lane, nrows, (int)(r0 - blk_lo), kPerLane * lane, gt_c0, gt_c1, rg_c0, rg_c1,
                                          scale, acc0, acc1);
         if (PENDING) fence_async_smem();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
@@ -255,7 +262,7 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
 }
 
 // grid = (column blocks, row segments); block = 32 threads.
-template <int kRows, int kStages>
+template <int kCols, int kRows, int kStages>
 __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUtensorMap map, const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
@@ -268,18 +275,22 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     if (row_lo < row_hi) {
         const int pending = a.sc->pending;
         const double scale = a.sc->scale;
-        if (!pending) sweep_body<kRows, kStages, false, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
-        else if (scale == 1.0) sweep_body<kRows, kStages, true, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
-        else sweep_body<kRows, kStages, true, true>(&map, a, row_lo, row_hi, scale, smem_raw, acc0, acc1);
+        if (!pending) sweep_body<kCols, kRows, kStages, false, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
+        else if (scale == 1.0) sweep_body<kCols, kRows, kStages, true, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
+        else sweep_body<kCols, kRows, kStages, true, true>(&map, a, row_lo, row_hi, scale, smem_raw, acc0, acc1);
     }
     if (!a.exchange) return;   // flush: only the deferred rank-1 was wanted
 
     // ---- tail: the last row segment of a column block sums the segments in order and publishes the block
-    const long long cl = (long long)cb * kCols + 2 * lane;   // local column of this lane
+    constexpr int kPerLane = kCols == 64 ? 2 : 1;
+    const bool lane_on = kCols >= 32 || lane < kCols;
+    const long long cl = (long long)cb * kCols + kPerLane * (lane_on ? lane : 0);   // local column of this lane
     if (a.nseg > 1) {
         double* out = a.partial + (long long)seg * a.ld_part;
-        out[cl] = acc0;          // ld_part is a multiple of 64: always in range
-        out[cl + 1] = acc1;
+        if (lane_on) {
+            out[cl] = acc0;          // ld_part is a multiple of the block width: always in range
+            if (kPerLane == 2) out[cl + 1] = acc1;
+        }
         __threadfence();
         unsigned prev = 0;
         if (lane == 0) prev = atomicAdd(&a.cnt_block[cb], 1u);
@@ -288,21 +299,21 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
         if (lane == 0) a.cnt_block[cb] = 0;
         __threadfence();
         acc0 = __ldcg(a.partial + cl);
-        acc1 = __ldcg(a.partial + cl + 1);
+        acc1 = kPerLane == 2 ? __ldcg(a.partial + cl + 1) : 0.0;
         for (int s = 1; s < a.nseg; ++s) {   // segment order: deterministic
             acc0 += __ldcg(a.partial + (long long)s * a.ld_part + cl);
-            acc1 += __ldcg(a.partial + (long long)s * a.ld_part + cl + 1);
+            if (kPerLane == 2) acc1 += __ldcg(a.partial + (long long)s * a.ld_part + cl + 1);
         }
     }
+    const bool v0 = lane_on && cl < a.w, v1 = kPerLane == 2 && cl + 1 < a.w;
     if (a.out) {   // Arr::dot_mv for its own sake (power iteration, conjugate gradient): no exchange, no state
-        if (cl < a.w) a.out[cl] = acc0;
-        if (cl + 1 < a.w) a.out[cl + 1] = acc1;
+        if (v0) a.out[cl] = acc0;
+        if (v1) a.out[cl + 1] = acc1;
         return;
     }
     const unsigned long long epoch = a.sc->epoch;
     const int attached = a.pt.nranks > 0;
     const long long off = (attached ? (long long)(epoch & 1ULL) * a.n : 0) + a.c_glob0 + cl;
-    const bool v0 = cl < a.w, v1 = cl + 1 < a.w;
     if (!attached) {
         if (v0) a.own_blk[off] = acc0;
         if (v1) a.own_blk[off + 1] = acc1;
@@ -514,7 +525,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols, long long ld, int box_rows) {
+int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -525,7 +536,7 @@ int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)kCols, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (const char* e = getenv("ELLCUDA_L2PROMO")) {   // performance experiments
@@ -542,7 +553,7 @@ int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols
     return ELLCUDA_OK;
 }
 
-constexpr size_t sweep_smem(int rows, int stages) { return (size_t)stages * (kCols * rows * 8 + rows * 24) + stages * 8 + 128; }
+constexpr size_t sweep_smem(int cols, int rows, int stages) { return (size_t)stages * (cols * rows * 8 + rows * 24) + stages * 8 + 128; }
 
 }  // namespace
 }  // namespace ellcuda
@@ -557,6 +568,7 @@ struct ellcuda_ctx {
     long long n = 0, w = 0, c0 = 0, ld = 0, npad = 0, ld_part = 0, ncb = 0;
     int nseg = 1, reduce_mode = 0, no_defer = 0, use_parallel = 1;
     int tile_rows = ellcuda::kRowsDefault, stages = ellcuda::kStagesDefault;   // sweep tile shape (ELLCUDA_SWEEP=rows,stages)
+    int cols = ellcuda::kColsMax;   // columns per sweep warp: 64, 32 or 16 (chosen so that enough warps stream)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     double* S = nullptr;        // n × ld, column block [c0, c0+w) of the symmetric matrix
@@ -567,7 +579,7 @@ struct ellcuda_ctx {
     const double* gsrc = nullptr;   // gradient of the update in flight (read again by finish)
     int* status_host = nullptr; // pinned, CutStatus read-back
     double* xblk = nullptr;     // exchange block (IPC-shareable cudaMalloc): grad_t[2][n], flags, omega parts
-    double2* pend = nullptr;    // npad + kCols + 2: deferred rank-1 vectors {grad_t, ratio·grad_t}
+    double2* pend = nullptr;    // npad + kColsMax + 2: deferred rank-1 vectors {grad_t, ratio·grad_t}
     double* partial = nullptr;  // nseg × ld_part
     double* block_omega = nullptr;  // ncb
     unsigned* counters = nullptr;   // ncb (per column block) + 1 (blocks done) + 1 (finish CTAs arrived)
@@ -613,9 +625,17 @@ int alloc_ctx(ellcuda_ctx* h) {
     }
     h->ld = (h->w + 1) & ~1LL;  // TMA needs a 16-byte row pitch
     h->npad = (n + kRowsMax - 1) / kRowsMax * kRowsMax + kRowsMax;
-    h->ld_part = (h->w + kCols - 1) / kCols * kCols;
-    h->ncb = h->ld_part / kCols;
-    const size_t pend_n = (size_t)(h->npad + kCols + 2);
+    // column-block width: the widest of 64 / 32 / 16 that still gives ~192 sweep warps (all resident, 2-3 per SM)
+    h->cols = kColsMax;
+    while (h->cols > 16 && ((h->w + h->cols - 1) / h->cols) * h->nseg < 192) h->cols /= 2;
+    if (const char* e = getenv("ELLCUDA_COLS")) {   // performance experiments
+        const int c = atoi(e);
+        if (c == 16 || c == 32 || c == 64) h->cols = c;
+    }
+    if (h->cols != kColsMax) { h->tile_rows = 64; h->stages = h->cols == 32 ? 4 : 6; }
+    h->ld_part = (h->w + kColsMax - 1) / kColsMax * kColsMax;
+    h->ncb = (h->w + h->cols - 1) / h->cols;
+    const size_t pend_n = (size_t)(h->npad + kColsMax + 2);
     ELL_CUDA_TRY(cudaMalloc(&h->S, (size_t)n * h->ld * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->xc, (size_t)n * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->gpad, (size_t)h->npad * 8));
@@ -637,29 +657,31 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMemset(h->pend, 0, pend_n * 16));
     ELL_CUDA_TRY(cudaMemset(h->counters, 0, (size_t)(h->ncb + 2) * 4));
     keep_mempool(h->device);
-    return make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows);
+    return make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows, h->cols);
 }
 
-template <int R, int ST>
+template <int CO, int R, int ST>
 int launch_sweep_t(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {
     static bool attr_set = false;   // per instantiation
-    constexpr size_t smem = sweep_smem(R, ST);
+    constexpr size_t smem = sweep_smem(CO, R, ST);
     if (!attr_set) {
-        ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<CO, R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    sweep_kernel<R, ST><<<grid, 32, smem, s>>>(h->map, a);
+    sweep_kernel<CO, R, ST><<<grid, 32, smem, s>>>(h->map, a);
     return ELLCUDA_OK;
 }
 
-int launch_sweep(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {   // tile rows x ring depth (ELLCUDA_SWEEP, experiments)
-    const int key = h->tile_rows * 100 + h->stages;
+int launch_sweep(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {
+    if (h->cols == 32) return launch_sweep_t<32, 64, 4>(h, grid, a, s);
+    if (h->cols == 16) return launch_sweep_t<16, 64, 6>(h, grid, a, s);
+    const int key = h->tile_rows * 100 + h->stages;   // 64-column blocks: tile rows x ring depth (ELLCUDA_SWEEP, experiments)
     switch (key) {
-        case 1608: return launch_sweep_t<16, 8>(h, grid, a, s);
-        case 3204: return launch_sweep_t<32, 4>(h, grid, a, s);
-        case 3206: return launch_sweep_t<32, 6>(h, grid, a, s);
-        case 4804: return launch_sweep_t<48, 4>(h, grid, a, s);
-        default: return launch_sweep_t<64, 3>(h, grid, a, s);
+        case 1608: return launch_sweep_t<64, 16, 8>(h, grid, a, s);
+        case 3204: return launch_sweep_t<64, 32, 4>(h, grid, a, s);
+        case 3206: return launch_sweep_t<64, 32, 6>(h, grid, a, s);
+        case 4804: return launch_sweep_t<64, 48, 4>(h, grid, a, s);
+        default: return launch_sweep_t<64, 64, 3>(h, grid, a, s);
     }
 }
 
@@ -874,7 +896,7 @@ int ellcuda_clone(ell_handle h, ell_handle* out) {
     Scal sc_h;
     e = cudaMemcpyAsync(c->S, h->S, (size_t)n * h->ld * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->xc, h->xc, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->pend, h->pend, (size_t)(h->npad + kCols + 2) * 16, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->pend, h->pend, (size_t)(h->npad + kColsMax + 2) * 16, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&sc_h, h->sc, sizeof(Scal), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     sc_h.epoch = 1;
