@@ -436,6 +436,7 @@ int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_
         else if (v == 1) rc = launch_one<OrLowpass<true, 2>, true, 8, 1>(a, s, sm_count);
         else if (v == 2) rc = launch_one<OrLowpass<true, 1>, true, 16, 1>(a, s, sm_count);
         else if (v == 3) rc = launch_one<OrLowpass<true, 1, false>, true, 8, 1>(a, s, sm_count);   // x re-read per round: 404
+        // (9 or 10 warps are allocated like 12: 168 registers, spills: 274 / 296 M iter/s)
         else rc = launch_one<OrLowpass<true, 1, true>, true, 8, 1>(a, s, sm_count);   // x held across the band sweeps: 413 M iter/s
     } else {
         set_error("oracle not available in the warp-per-problem kernel");
