@@ -73,7 +73,7 @@ struct OrBowl {  // tests/integration_test.rs:90-105
     static constexpr bool kNeedsTable = false;
 };
 
-template <bool FIXED32, int kRowsPerLane, bool XREG = false>
+template <bool FIXED32, int kRowsPerLane, bool XREG = false, int kUnroll = 4>
 struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
     int idx1, idx2, idx3, nwpass, nwstop, mdim, kmax;
     double lp_sq, up_sq, sp_sq, fmax;
@@ -106,7 +106,7 @@ struct OrLowpass {  // src/oracles/lowpass_oracle.rs:7-150
                 for (int r = 0; r < R; ++r) acc[r] += row[r][j] * xr[j];
             }
         } else if constexpr (FIXED32) {
-#pragma unroll
+#pragma unroll kUnroll
             for (int j = 0; j < 32; j += 2) {
                 const double2 x = *reinterpret_cast<const double2*>(c.sx() + j);
 #pragma unroll
@@ -428,16 +428,16 @@ int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_
             return ELLCUDA_E_ARG;
         }
         const int v = tuning_variant();
-        // Measured on B200 (tools/probe_tune.py, 16384 problems): rows-per-lane R x warps-per-CTA W ->
-        //   R1W8 402 M iter/s (196 regs, no spills) | R2W8 396 | R3W8 363 | R4W8 317 | R1W16 354 (128 regs, spills) | R1W12 333.
-        // The kernel is bound by shared-memory bandwidth (spectrum rows: 256 B per lane per row), so extra
-        // speculative rows (R>1) cost more than the latency they hide, and 8 warps already saturate the LSU.
+        // Measured on B200 (tools/probe_tune.py, 16384 problems; R = rows per lane per round, W = warps per CTA, U = unroll
+        // of the row-dot loop):  R1 W16 U8  448 M iter/s (128 regs, 44 B spilled)  <- default
+        //   R1 W16 U4 436 | U2 428 | U1 398 | U16 354 (970 B spilled) | R1 W12 U4 418 | R1 W8 x-in-registers 412 (196 regs)
+        //   R1 W8 U16 404 | R2 W8 396 | R3 W8 363 | R4 W8 317 | 9-10 warps are allocated like 12 (168 regs, spills): 274-296.
+        // The kernel is bound by shared-memory bandwidth (spectrum rows: 256 B per lane per row), so extra speculative
+        // rows (R>1) cost more than the latency they hide; what pays is more resident warps without spilling.
         if (a.n != 32) rc = launch_one<OrLowpass<false, 1>, false, 8, 1>(a, s, sm_count);
-        else if (v == 1) rc = launch_one<OrLowpass<true, 2>, true, 8, 1>(a, s, sm_count);
-        else if (v == 2) rc = launch_one<OrLowpass<true, 1>, true, 16, 1>(a, s, sm_count);
-        else if (v == 3) rc = launch_one<OrLowpass<true, 1, false>, true, 8, 1>(a, s, sm_count);   // x re-read per round: 404
-        // (9 or 10 warps are allocated like 12: 168 registers, spills: 274 / 296 M iter/s)
-        else rc = launch_one<OrLowpass<true, 1, true>, true, 8, 1>(a, s, sm_count);   // x held across the band sweeps: 413 M iter/s
+        else if (v == 1) rc = launch_one<OrLowpass<true, 2, false, 16>, true, 8, 1>(a, s, sm_count);
+        else if (v == 2) rc = launch_one<OrLowpass<true, 1, true>, true, 8, 1>(a, s, sm_count);
+        else rc = launch_one<OrLowpass<true, 1, false, 8>, true, 16, 1>(a, s, sm_count);
     } else {
         set_error("oracle not available in the warp-per-problem kernel");
         return ELLCUDA_E_ARG;
