@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node P tools/check_sharded.py — NCCL row-sharded Ell against the CPU checker (bit for bit in
+"""torchrun --nproc-per-node P tests/multi_gpu_check.py — NCCL row-sharded Ell against the CPU checker (bit for bit in
 reduce_mode 0, 1e-9 in reduce_mode 4) and problem-sharded batch against the single-rank result."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
