@@ -220,7 +220,9 @@ int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev);
 int ellcuda_update(ell_handle h, int32_t which, const double* grad_host,
                    double beta0, int32_t has_beta1, double beta1, int32_t* out_status);
 
-/* Same, split for sharded / device-resident use.  `grad_dev` is device memory (n values).
+/* Same, split for sharded / device-resident use.  `grad_dev` is device memory (n values) and must stay valid and
+ * unchanged until the matching ellcuda_update_finish has run on the stream (both kernels read it; when n is a
+ * multiple of 64 and the pointer is 16-byte aligned it is read in place, otherwise a padded copy is made).
  *   begin : applies the previous cut's deferred rank-1 to this slab and, in the same sweep
  *           over M, forms this slab's part of grad_t = M·grad   (ell.rs:102, 117-128)
  *   (exchange: every rank needs all n entries of grad_t — allgather of
@@ -231,7 +233,7 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host,
 int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev,
                          double beta0, int32_t has_beta1, double beta1);
 int ellcuda_update_finish(ell_handle h);
-double*  ellcuda_grad_t_ptr(ell_handle h);   /* device, n doubles (the buffer of the most recent begin)   */
+double*  ellcuda_grad_t_ptr(ell_handle h);   /* device, n doubles: grad_t of handles without peer exchange  */
 
 /* Peer exchange over NVLink without NCCL (one process per GPU).  Every rank exports its exchange block
  * (ELLCUDA_IPC_HANDLE_BYTES opaque bytes, a CUDA IPC handle), the P handles are gathered by any means
