@@ -435,6 +435,7 @@ int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_
         // The kernel is bound by shared-memory bandwidth (spectrum rows: 256 B per lane per row), so extra speculative
         // rows (R>1) cost more than the latency they hide; what pays is more resident warps without spilling.
         if (a.n != 32) rc = launch_one<OrLowpass<false, 1>, false, 8, 1>(a, s, sm_count);
+        else if (v == 0) return launch_batch_lowpass32(a, s, sm_count, launches);   // TMEM-assisted kernel, batch_lowpass.cu
         else if (v == 1) rc = launch_one<OrLowpass<true, 2, false, 16>, true, 8, 1>(a, s, sm_count);
         else if (v == 2) rc = launch_one<OrLowpass<true, 1, true>, true, 8, 1>(a, s, sm_count);
         else rc = launch_one<OrLowpass<true, 1, false, 8>, true, 16, 1>(a, s, sm_count);

@@ -71,6 +71,7 @@ struct DevGuard {
 // launchers implemented per kernel family; each returns ELLCUDA_* and adds to *launches
 int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
+int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, long long* launches);
 int launch_math_probe(int which, const double* x_dev, double* y_dev, long long n, cudaStream_t s);
 int launch_stable_single(double* qu_packed_upper, double* xc, double* scal_kappa_tsq, int* status, const double* g, int n,
                          int use_parallel_cut, int which, const Cut& cut, cudaStream_t s);
