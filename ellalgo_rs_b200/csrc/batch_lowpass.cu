@@ -8,7 +8,6 @@
 //   * M lives in TMEM between updates (lane i = row i, 64 columns per warp), not in registers;
 //   * that frees 64 registers during the oracle phase for x (read once per oracle call instead of once per round);
 //   * the last 8 of the 32 columns of every spectrum row come from TMEM, the first 24 from shared memory;
-//   * ratio*grad_t[j] is recomputed per lane (one DMUL, same operands, same rounding) instead of broadcast.
 // TMEM is lane-addressed: thread L of a warp reaches only lane 32*(warp%4)+L, at a warp-uniform column.  Spectrum row r
 // is therefore stored in lane r%32, column block r/32, and a round of 32 consecutive rows k0..k0+31 is evaluated with
 // thread L on the row whose index is congruent to L (traversal position p = (L - k0) mod 32).  The rows of a round
@@ -25,15 +24,13 @@
 namespace ellcuda {
 namespace {
 
-constexpr int kWarps = 16;
 constexpr int kN = 32;
 constexpr int kTabStride = 33;          // doubles per shared-memory row (odd: rows of one half-warp hit distinct banks)
 constexpr int kTmemCols = 512;
 constexpr int kMCols = 64;              // one M row per lane: 32 doubles
 constexpr int kTabCol0 = 4 * kMCols;    // 4 warps per lane quarter keep their M in columns [0, 256)
-constexpr int kTabTm = 8;               // trailing columns of each spectrum row held in TMEM
-constexpr int kTabBlkCols = 2 * kTabTm; // 32-bit columns per 32-row block
-constexpr int kScratch = 4 * 32;        // doubles per warp: sx | sg | sgt | sp
+constexpr int kTabBlkCols = 16;         // 32-bit columns per 32-row block of the spectrum tail (8 doubles per row)
+constexpr int kScratch = 5 * 32;        // doubles per warp: sx | sg | sgt | sp | srg
 
 // ---- tcgen05 load / store, shape 32x32b: thread L <-> TMEM lane (base lane + L), N consecutive 32-bit columns
 __device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -41,7 +38,7 @@ __device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
+        : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -115,6 +112,7 @@ struct Ctx {
     __device__ __forceinline__ double* sg() const { return ws + 32; }
     __device__ __forceinline__ double* sgt() const { return ws + 64; }
     __device__ __forceinline__ double* sp() const { return ws + 96; }
+    __device__ __forceinline__ double* srg() const { return ws + 128; }
 };
 
 __device__ __forceinline__ double seq_sum32(const double* s) {
@@ -128,6 +126,7 @@ __device__ __forceinline__ double seq_sum32(const double* s) {
     return acc;
 }
 
+template <int kTabTm>   // trailing columns of each spectrum row read from TMEM (0 or 8)
 struct Lowpass32 {  // src/oracles/lowpass_oracle.rs:7-150
     int idx1, idx2, idx3, nwpass, nwstop, mdim, kmax;
     double lp_sq, up_sq, sp_sq, fmax;
@@ -163,19 +162,23 @@ struct Lowpass32 {  // src/oracles/lowpass_oracle.rs:7-150
             const int q = k0 >> 5;
             const bool upper = (row >> 5) != q;
             uint32_t ta[16], tb[16];
-            tm_ld16(c.tm_tab + (uint32_t)(q * kTabBlkCols), ta);
-            tm_ld16(c.tm_tab + (uint32_t)((q + 1) * kTabBlkCols), tb);   // block 15 is allocated, never selected
+            if constexpr (kTabTm > 0) {
+                tm_ld16(c.tm_tab + (uint32_t)(q * kTabBlkCols), ta);
+                tm_ld16(c.tm_tab + (uint32_t)((q + 1) * kTabBlkCols), tb);   // block 15 is allocated, never selected
+            }
             const int srow = row < mdim ? row : row - 32;   // idle threads read a valid row of their own residue
             const double* rp = c.tab + srow * kTabStride;
             double val = 0.0;
 #pragma unroll
             for (int j = 0; j < kN - kTabTm; ++j) val += rp[j] * xr[j];
-            tm_wait_ld();
+            if constexpr (kTabTm > 0) {
+                tm_wait_ld();
 #pragma unroll
-            for (int j = 0; j < kTabTm; ++j) {
-                const uint32_t wlo = upper ? tb[2 * j] : ta[2 * j];
-                const uint32_t whi = upper ? tb[2 * j + 1] : ta[2 * j + 1];
-                val += mk_double(wlo, whi) * xr[kN - kTabTm + j];
+                for (int j = 0; j < kTabTm; ++j) {
+                    const uint32_t wlo = upper ? tb[2 * j] : ta[2 * j];
+                    const uint32_t whi = upper ? tb[2 * j + 1] : ta[2 * j + 1];
+                    val += mk_double(wlo, whi) * xr[kN - kTabTm + j];
+                }
             }
             bool viol;
             if (BAND == 0) viol = active && (val > up_sq || val < lp_sq);
@@ -251,6 +254,7 @@ struct Lowpass32 {  // src/oracles/lowpass_oracle.rs:7-150
     }
 };
 
+template <int kTabTm, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const BatchArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ uint32_t tmem_base_s;
@@ -270,12 +274,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
     tm_fence_sync();
     const uint32_t tm_base = tmem_base_s;
     const uint32_t tm_lane = tm_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    if (warp < 4) {   // one warp per lane quarter stores the tail columns of row 32*b + lane in column block b
+    if (kTabTm > 0 && warp < 4) {   // one warp per lane quarter stores the tail columns of row 32*b + lane in column block b
         for (int b = 0; b < rows / 32; ++b) {
             uint32_t r[16];
-            const double* src = smem + (32 * b + lane) * kTabStride + (kN - kTabTm);
+            const double* src = smem + (32 * b + lane) * kTabStride + (kN - 8);
 #pragma unroll
-            for (int j = 0; j < kTabTm; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 r[2 * j] = (uint32_t)__double2loint(src[j]);
                 r[2 * j + 1] = (uint32_t)__double2hiint(src[j]);
             }
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
         double kappa = a.kappa0[pid * a.kappa0_stride];
         double gamma = a.gamma0 ? a.gamma0[pid * a.gamma0_stride] : 0.0;
         double tsq = 0.0;
-        Lowpass32 om;
+        Lowpass32<kTabTm> om;
         om.init(a, pid);
 
         bool has_best = false;
@@ -357,13 +361,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
             xc -= rho_over_omega * gt;
             const double ratio = r.sigma / omega;
             const double rg = ratio * gt;
+            c.srg()[lane] = rg;
+            __syncwarp();
             // element (lane, j): hi = max(lane, j) supplies ratio*grad_t, lo = min(lane, j) supplies grad_t
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 const double2 gv = *reinterpret_cast<const double2*>(c.sgt() + j);
+                const double2 rv = *reinterpret_cast<const double2*>(c.srg() + j);
                 double u0, u1;
-                if (j <= lane) u0 = rg * gv.x; else u0 = (ratio * gv.x) * gt;
-                if (j + 1 <= lane) u1 = rg * gv.y; else u1 = (ratio * gv.y) * gt;
+                if (j <= lane) u0 = rg * gv.x; else u0 = rv.x * gt;
+                if (j + 1 <= lane) u1 = rg * gv.y; else u1 = rv.y * gt;
                 m[j] -= u0;
                 m[j + 1] -= u1;
             }
@@ -396,13 +403,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tm_base) : "memory");
 }
 
-}  // namespace
-
-int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, long long* launches) {
-    if (a.n != kN || a.aux[0] != 15 * kN) { set_error("lowpass32 kernel needs n = 32 and a 480-row spectrum"); return ELLCUDA_E_ARG; }
+template <int kTabTm, int kWarps>
+int launch_variant(const BatchArgs& a, cudaStream_t s, int sm_count) {
     const size_t tab = ((size_t)a.aux[0] * kTabStride + 1) & ~(size_t)1;
     const size_t smem = (tab + (size_t)kWarps * kScratch) * sizeof(double);
-    auto kern = lowpass32_tmem_kernel;
+    auto kern = lowpass32_tmem_kernel<kTabTm, kWarps>;
     ELL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks = sm_count;  // persistent: one CTA per SM (it owns the SM's 512 TMEM columns)
     const long long need = (a.count + kWarps - 1) / kWarps;
@@ -410,8 +415,23 @@ int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, lon
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, kWarps * 32, smem, s>>>(a);
     ELL_CUDA_TRY(cudaGetLastError());
-    if (launches) *launches += 1;
     return ELLCUDA_OK;
+}
+
+}  // namespace
+
+int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, long long* launches) {
+    if (a.n != kN || a.aux[0] != 15 * kN) { set_error("lowpass32 kernel needs n = 32 and a 480-row spectrum"); return ELLCUDA_E_ARG; }
+    const char* e = getenv("ELLCUDA_LOWPASS_VARIANT");   // performance experiments only; results are identical
+    const int v = e ? atoi(e) : 0;
+    int rc;
+    // Measured on B200 (tools/probe_tune.py, 16384 problems): spectrum entirely in shared memory 503 M iter/s (default);
+    // last 8 columns of every row from TMEM 490 (the two-block select costs more issue slots than the shared-memory
+    // wavefronts it saves); 20 warps x 96 registers 395 (spills).  batch_warp.cu's kernel (M in registers): 445.
+    if (v == 1) rc = launch_variant<8, 16>(a, s, sm_count);
+    else rc = launch_variant<0, 16>(a, s, sm_count);
+    if (rc == ELLCUDA_OK && launches) *launches += 1;
+    return rc;
 }
 
 }  // namespace ellcuda
