@@ -426,15 +426,16 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
             "iterations_per_step_per_gpu": iters_step,
-            "roofline": {"bound": "hbm", "kernel": "batch_warp_kernel<OrLowpass> (persistent, one warp per problem)",
+            "roofline": {"bound": "hbm", "kernel": "lowpass32_tmem_kernel (persistent, one warp per problem, M in tensor memory)",
                          "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                          "ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         # real DRAM traffic is inputs + results only: ncu (4736-problem launch, profiles/r01b_prof_batch2_raw.csv)
-                         # read 0.45 MB, wrote < 1 MB — scaled by problem count here, not re-measured per run
+                         # real DRAM traffic is inputs + results only: ncu (4736-problem launch, profiles/r01c_prof_batch5_raw.csv)
+                         # read 0.75 MB, wrote < 1 MB — scaled by problem count here, not re-measured per run
                          "traffic": float(h2d + d2h),
                          "note": "equivalent-streaming figure of SURVEY.md 8d: 16*n^2 bytes per iteration (M read once, written "
-                                 "once) although M never leaves the register file; see large_n.roofline for the kernel that "
+                                 "once) although M never leaves the SM (tensor memory + registers); the binding resource is the shared-memory "
+                                 "data pipe (80 %, profiles/r01c_prof_batch5_summary.txt); see large_n.roofline for the kernel that "
                                  "really streams HBM"},
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps},

@@ -126,7 +126,9 @@ __device__ __forceinline__ double seq_sum32(const double* s) {
     return acc;
 }
 
-template <int kTabTm>   // trailing columns of each spectrum row read from TMEM (0 or 8)
+// kTabTm: trailing columns of each spectrum row read from TMEM (0 or 8).  kAligned: rounds end at multiples of 32 rows, so
+// the rows of a round share one TMEM column block (one load, no per-thread select) at the price of more, partly idle rounds.
+template <int kTabTm, bool kAligned>
 struct Lowpass32 {  // src/oracles/lowpass_oracle.rs:7-150
     int idx1, idx2, idx3, nwpass, nwstop, mdim, kmax;
     double lp_sq, up_sq, sp_sq, fmax;
@@ -156,15 +158,16 @@ struct Lowpass32 {  // src/oracles/lowpass_oracle.rs:7-150
             if (seg > 32) seg = 32;
             if (seg > len - done) seg = len - done;
             const int rot = k0 & 31;
+            if (kAligned && seg > 32 - rot) seg = 32 - rot;
             const int p = (c.lane - rot) & 31;          // traversal position of this thread's row inside the round
             const int row = k0 + p;                     // congruent to lane mod 32
             const bool active = p < seg;
             const int q = k0 >> 5;
-            const bool upper = (row >> 5) != q;
+            const bool upper = !kAligned && (row >> 5) != q;
             uint32_t ta[16], tb[16];
             if constexpr (kTabTm > 0) {
                 tm_ld16(c.tm_tab + (uint32_t)(q * kTabBlkCols), ta);
-                tm_ld16(c.tm_tab + (uint32_t)((q + 1) * kTabBlkCols), tb);   // block 15 is allocated, never selected
+                if constexpr (!kAligned) tm_ld16(c.tm_tab + (uint32_t)((q + 1) * kTabBlkCols), tb);   // block 15 is allocated, never selected
             }
             const int srow = row < mdim ? row : row - 32;   // idle threads read a valid row of their own residue
             const double* rp = c.tab + srow * kTabStride;
@@ -175,8 +178,8 @@ struct Lowpass32 {  // src/oracles/lowpass_oracle.rs:7-150
                 tm_wait_ld();
 #pragma unroll
                 for (int j = 0; j < kTabTm; ++j) {
-                    const uint32_t wlo = upper ? tb[2 * j] : ta[2 * j];
-                    const uint32_t whi = upper ? tb[2 * j + 1] : ta[2 * j + 1];
+                    const uint32_t wlo = (!kAligned && upper) ? tb[2 * j] : ta[2 * j];
+                    const uint32_t whi = (!kAligned && upper) ? tb[2 * j + 1] : ta[2 * j + 1];
                     val += mk_double(wlo, whi) * xr[kN - kTabTm + j];
                 }
             }
@@ -254,7 +257,7 @@ struct Lowpass32 {  // src/oracles/lowpass_oracle.rs:7-150
     }
 };
 
-template <int kTabTm, int kWarps>
+template <int kTabTm, bool kAligned, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const BatchArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ uint32_t tmem_base_s;
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
         double kappa = a.kappa0[pid * a.kappa0_stride];
         double gamma = a.gamma0 ? a.gamma0[pid * a.gamma0_stride] : 0.0;
         double tsq = 0.0;
-        Lowpass32<kTabTm> om;
+        Lowpass32<kTabTm, kAligned> om;
         om.init(a, pid);
 
         bool has_best = false;
@@ -403,11 +406,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tm_base) : "memory");
 }
 
-template <int kTabTm, int kWarps>
+template <int kTabTm, bool kAligned, int kWarps>
 int launch_variant(const BatchArgs& a, cudaStream_t s, int sm_count) {
     const size_t tab = ((size_t)a.aux[0] * kTabStride + 1) & ~(size_t)1;
     const size_t smem = (tab + (size_t)kWarps * kScratch) * sizeof(double);
-    auto kern = lowpass32_tmem_kernel<kTabTm, kWarps>;
+    auto kern = lowpass32_tmem_kernel<kTabTm, kAligned, kWarps>;
     ELL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks = sm_count;  // persistent: one CTA per SM (it owns the SM's 512 TMEM columns)
     const long long need = (a.count + kWarps - 1) / kWarps;
@@ -427,9 +430,11 @@ int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, lon
     int rc;
     // Measured on B200 (tools/probe_tune.py, 16384 problems): spectrum entirely in shared memory 503 M iter/s (default);
     // last 8 columns of every row from TMEM 490 (the two-block select costs more issue slots than the shared-memory
-    // wavefronts it saves); 20 warps x 96 registers 395 (spills).  batch_warp.cu's kernel (M in registers): 445.
-    if (v == 1) rc = launch_variant<8, 16>(a, s, sm_count);
-    else rc = launch_variant<0, 16>(a, s, sm_count);
+    // wavefronts it saves); the same with block-aligned rounds (one TMEM load, no select, 5.04 rounds per call) 482;
+    // 20 warps x 96 registers 395 (spills).  batch_warp.cu's kernel (M in registers): 445.
+    if (v == 1) rc = launch_variant<8, false, 16>(a, s, sm_count);
+    else if (v == 2) rc = launch_variant<8, true, 16>(a, s, sm_count);
+    else rc = launch_variant<0, false, 16>(a, s, sm_count);
     if (rc == ELLCUDA_OK && launches) *launches += 1;
     return rc;
 }

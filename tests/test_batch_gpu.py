@@ -289,6 +289,55 @@ def test_lowpass_flags_and_per_instance_kappa(ref):
         assert_parity(g, r, exact=True, what=f"lowpass {kw}")
 
 
+def _lowpass_band_cases(t):
+    """band layouts that stress the 32-row rounds of the TMEM kernel: bands shorter than a round, an empty transition
+    band (wstop == wpass), pass-band of one row, band edges on and next to multiples of 32, a stop-band of 2 rows"""
+    prob = W.lowpass(9, t, max_iters=1500)
+    p = prob.params
+    edges = [(0.001, 0.002), (0.12, 0.12), (31.5 / 479, 63.5 / 479), (32.5 / 479, 64.5 / 479), (0.30, 0.31),
+             (0.05, 0.995), (0.90, 0.9979), (63.5 / 479, 95.5 / 479), (0.49, 0.51)]
+    for i, (wp, ws) in enumerate(edges):
+        p[i, 0], p[i, 1] = wp, ws
+    return prob
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_lowpass32_tmem_kernel_band_layouts_and_initial_matrices(ref, variant, monkeypatch):
+    """batch_lowpass.cu: both variants (spectrum in shared memory / tail columns in TMEM) against the checker on awkward
+    band layouts, and with Ell::new (diag0) and Ell::new_with_matrix (mq0) starts, which go through the TMEM store path"""
+    monkeypatch.setenv("ELLCUDA_LOWPASS_VARIANT", variant)
+    t = batch.lowpass_table(32)
+    g, r = both(ref, _lowpass_band_cases(t))
+    assert_parity(g, r, exact=True, what=f"lowpass band layouts, variant {variant}")
+    rng = np.random.default_rng(7)
+    prob = W.lowpass(5, t, max_iters=800)
+    prob.kappa0 = np.full(5, 1.0)
+    prob.diag0 = 20.0 + 40.0 * rng.random((5, 32))
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"lowpass diag0, variant {variant}")
+    prob = W.lowpass(3, t, max_iters=800)
+    a = rng.standard_normal((3, 32, 32)) * 0.1
+    spd = np.einsum("pij,pkj->pik", a, a) + np.eye(32)[None]
+    prob.mq0 = np.ascontiguousarray(0.5 * (spd + spd.transpose(0, 2, 1)))     # exactly symmetric (the C ABI checks it)
+    prob.kappa0 = np.full(3, 30.0)
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"lowpass mq0, variant {variant}")
+
+
+def test_lowpass32_more_problems_than_resident_warps(ref):
+    """the persistent kernel's queue: 148 SMs x 16 warps = 2368 resident problems; 2600 short problems must all come back,
+    equal to the checker's first 64 and to a re-run"""
+    t = batch.lowpass_table(32)
+    prob = W.lowpass(2600, t, max_iters=40)
+    g1 = batch.solve_batch(prob)
+    g2 = batch.solve_batch(prob)
+    assert np.array_equal(g1.num_iters, g2.num_iters) and np.array_equal(g1.xc, g2.xc)
+    assert (g1.exit_status > 0).all()
+    small = W.lowpass(64, t, max_iters=40)
+    r = ref.solve(small)
+    assert np.array_equal(g1.num_iters[:64], r.num_iters) and np.array_equal(g1.xc[:64], r.xc)
+
+
 def test_non_finite_inputs_propagate_like_the_reference(ref):
     """no guard is added that the reference does not have: NaN / inf centres give the same status"""
     prob = W.bowl(4, n=32, max_iters=50)
