@@ -20,7 +20,8 @@ MODE_OPTIM, MODE_FEAS, MODE_OPTIM_Q, MODE_BSEARCH = 0, 1, 2, 3
 
 (ORACLE_EXAMPLE1, ORACLE_EXAMPLE1_RR, ORACLE_EXAMPLE4, ORACLE_QUASICVX, ORACLE_PROFIT,
  ORACLE_PROFIT_RB, ORACLE_PROFIT_Q, ORACLE_LOWPASS, ORACLE_BOWL, ORACLE_LMI, ORACLE_EXAMPLE2,
- ORACLE_EXAMPLE3, ORACLE_HALFPLANE, ORACLE_ALWAYS_CUT, ORACLE_OPTIM_BOX, ORACLE_LMI_LINOPT) = range(16)
+ ORACLE_EXAMPLE3, ORACLE_HALFPLANE, ORACLE_ALWAYS_CUT, ORACLE_OPTIM_BOX, ORACLE_LMI_LINOPT, ORACLE_LMI_OLD,
+ ORACLE_LMI0) = range(18)
 
 _pd = C.POINTER(C.c_double)
 

@@ -54,6 +54,7 @@ struct LmiShared {
     const double* fp;  // n × fstride packed lower triangles of F_k
     const double* bp;  // tri packed lower triangle of B
     int fstride, m, tri, nvar;
+    int lmi0;          // LMI0Oracle (lmi0_oracle.rs:17-34): elements start from 0.0 and ADD F_k*x_k; gradient negated; no B
 };
 
 // returns true if a cut was produced: g0/g1 = this lane's gradient entries, ep = beta
@@ -65,15 +66,27 @@ __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, doub
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = e0 + 32 * u;
-            a[u] = e < tri ? L.bp[e] : 0.0;
+            a[u] = (e < tri && !L.lmi0) ? L.bp[e] : 0.0;
         }
-        for (int k = 0; k < n; ++k) {
-            const double xk = wm.sx[k];
-            const double* fk = L.fp + k * L.fstride;
+        if (!L.lmi0) {
+            for (int k = 0; k < n; ++k) {
+                const double xk = wm.sx[k];
+                const double* fk = L.fp + k * L.fstride;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + 32 * u;
-                if (e < tri) a[u] -= fk[e] * xk;
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + 32 * u;
+                    if (e < tri) a[u] -= fk[e] * xk;
+                }
+            }
+        } else {
+            for (int k = 0; k < n; ++k) {
+                const double xk = wm.sx[k];
+                const double* fk = L.fp + k * L.fstride;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + 32 * u;
+                    if (e < tri) a[u] += fk[e] * xk;
+                }
             }
         }
 #pragma unroll
@@ -141,6 +154,7 @@ __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, doub
             e += j + 1;
         }
     }
+    if (L.lmi0) { r0 = -r0; r1 = -r1; }   // g[k] = -sym_quad(F_k), lmi0_oracle.rs:31
     g0 = k0 < n ? r0 : 0.0;
     g1 = k1 < n ? r1 : 0.0;
     return true;
@@ -242,7 +256,7 @@ __device__ int stable_update(const CalcConsts& cc, int which, const WarpMem& wm,
 
 // ---------------------------------------------------------------------------------------------- kernel
 template <bool DIAG, int MAXT>
-__global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, int warps, int fstride, int per_warp_doubles) {
+__global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, int warps, int fstride, int per_warp_doubles, int lmi0) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n, m = a.aux[0], tri = m * (m + 1) / 2;
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, i
         while (tri_index(i + 1, 0) <= e) ++i;
         while (tri_index(i, 0) > e) --i;
         const int j = e - tri_index(i, 0);
-        bp[e] = a.table[(long long)n * m * m + i * m + j];
+        bp[e] = lmi0 ? 0.0 : a.table[(long long)n * m * m + i * m + j];
     }
     __syncthreads();
     long long base = (long long)n * fstride + tri;
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, i
     wm.st = wm.sa + ((tri + 1) & ~1);
     wm.swit = wm.st + m * m;
     wm.qu = wm.swit + ((m + 1) & ~1);
-    LmiShared L{fp, bp, fstride, m, tri, n};
+    LmiShared L{fp, bp, fstride, m, tri, n, lmi0};
     const CalcConsts cc = CalcConsts::make(n, a.use_parallel_cut);
     const int i0 = lane, i1 = lane + 32;
     const bool on0 = i0 < n, on1 = i1 < n;
@@ -388,7 +402,13 @@ int launch_stable_single(double* qu, double* xc, double* scal, int* status, cons
 }
 
 int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
-    if (oracle_id != ELL_ORACLE_LMI) { set_error("this oracle has no device implementation yet"); return ELLCUDA_E_ARG; }
+    if (oracle_id != ELL_ORACLE_LMI && oracle_id != ELL_ORACLE_LMI_OLD && oracle_id != ELL_ORACLE_LMI0) {
+        set_error("this oracle has no device implementation yet");
+        return ELLCUDA_E_ARG;
+    }
+    // LMI_OLD: the reference builds all m*m elements (k outermost) and then factorizes; every element undergoes the same
+    // operations in the same order as in LMIOracle's lazy closure, so the lazy kernel is its exact equivalent.
+    const int lmi0 = oracle_id == ELL_ORACLE_LMI0;
     if (a.kind != ELL_KIND_ELLSTABLE || a.mode != ELL_MODE_FEAS) {
         set_error("the LMI device oracle runs under cutting_plane_feas with EllStable");
         return ELLCUDA_E_ARG;
@@ -396,7 +416,10 @@ int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int s
     const int n = a.n, m = a.aux[0];
     if (n < 1 || n > kNMax) { set_error("LMI kernel needs 1 <= n <= 64"); return ELLCUDA_E_ARG; }
     if (m < 1 || m > 32) { set_error("LMI kernel needs 1 <= m <= 32"); return ELLCUDA_E_ARG; }
-    if (!a.table || a.table_len < (long long)(n + 1) * m * m) { set_error("LMI needs table = F_0..F_{n-1}, B"); return ELLCUDA_E_ARG; }
+    if (!a.table || a.table_len < (long long)(n + (lmi0 ? 0 : 1)) * m * m) {
+        set_error(lmi0 ? "LMI0 needs table = F_0..F_{n-1}" : "LMI needs table = F_0..F_{n-1}, B");
+        return ELLCUDA_E_ARG;
+    }
     const int tri = m * (m + 1) / 2;
     const int fstride = tri | 1;
     const bool diag = a.mq0 == nullptr;
@@ -422,7 +445,7 @@ int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int s
     if (blocks < 1) blocks = 1;
     auto launch = [&](auto kern) -> int {
         ELL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)blocks, warps * 32, smem, s>>>(a, warps, fstride, per_warp);
+        kern<<<(unsigned)blocks, warps * 32, smem, s>>>(a, warps, fstride, per_warp, lmi0);
         return ELLCUDA_OK;
     };
     int rc;

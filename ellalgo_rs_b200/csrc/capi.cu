@@ -137,7 +137,8 @@ static int batch_solve_impl(const ell_batch_desc* d, const ell_batch_result* r) 
         return ELLCUDA_E_ARG;
     }
 
-    if (d->oracle_id == ELL_ORACLE_LMI && !d->on_device && d->table) {
+    if ((d->oracle_id == ELL_ORACLE_LMI || d->oracle_id == ELL_ORACLE_LMI_OLD || d->oracle_id == ELL_ORACLE_LMI0) && !d->on_device &&
+        d->table) {
         // the device keeps F_k as packed lower triangles; sym_quad (ldlt_mgr.rs:115-124) reads both triangles, so the
         // F_k must be symmetric — which an LMI requires anyway
         const long long m = d->aux[0];
@@ -221,6 +222,8 @@ static int batch_solve_impl(const ell_batch_desc* d, const ell_batch_result* r) 
             rc = launch_batch_warp(a, d->oracle_id, s, di->sm_count, &g_last_launches);
             break;
         case ELL_ORACLE_LMI:
+        case ELL_ORACLE_LMI_OLD:
+        case ELL_ORACLE_LMI0:
             rc = launch_batch_stable(a, d->oracle_id, s, di->sm_count, &g_last_launches);
             break;
         default:

@@ -116,6 +116,18 @@ def lmi(count: int, n: int = 64, m: int = 16, first: int = 0, general: bool = Fa
                         kappa0=100.0, xc0=xc0, mq0=mq0, table=table, aux=[m], max_iters=2000, tolerance=1e-20)
 
 
+def lmi0(count: int, n: int = 64, m: int = 16, first: int = 0) -> BatchProblem:
+    """LMI0Oracle (src/oracles/lmi0_oracle.rs) as a feasibility problem: find x with sum_k F_k x_k > 0.  F_0 = I +
+    0.25*sym(U[-1,1]) keeps the cone non-trivial (x = e_0 is inside), the other F_k are lmi_table's; EllStable::
+    new_with_scalar(100, xc0), xc0 in U[-1,1]^n."""
+    tab = lmi_table(n, m)[: n * m * m].copy()
+    f0 = tab[: m * m].reshape(m, m)
+    tab[: m * m] = (np.eye(m) + 0.25 * f0).reshape(-1)
+    xc0 = _uniform(SEED + 8, count, n, -1.0, 1.0, first)
+    return BatchProblem(oracle_id=_abi.ORACLE_LMI0, n=n, count=count, mode=_abi.MODE_FEAS, kind=_abi.KIND_ELLSTABLE,
+                        kappa0=100.0, xc0=xc0, table=tab, aux=[m], max_iters=2000, tolerance=1e-20)
+
+
 def large_n_grad(n: int, k: int) -> np.ndarray:
     """C5: cut k of the n-dimensional single ellipsoid, g_k[j] = (2u-1)/sqrt(n)."""
     u = splitmix_u01(SEED + 8, np.uint64(k) * np.uint64(n) + np.arange(n, dtype=np.uint64))

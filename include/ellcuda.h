@@ -98,7 +98,13 @@ extern "C" {
                                      LMI blocks, round-robin.  table = c[n], then per block
                                      F_0..F_{n-1}, B;  aux[0] = L, aux[1..L] = block sizes
                                      (device: n = 3, L <= 3, block size <= 4)               */
-#define ELL_ORACLE_COUNT       16
+#define ELL_ORACLE_LMI_OLD     16 /* src/oracles/lmi_old_oracle.rs:5-50  feas; table and aux as ELL_ORACLE_LMI.  The
+                                     reference forms all of A = B - sum_k F_k x_k before factorizing; each element sees
+                                     the same operations in the same order, so results equal ELL_ORACLE_LMI's bit for bit
+                                     (the device evaluates only the elements the factorization asks for)             */
+#define ELL_ORACLE_LMI0        17 /* src/oracles/lmi0_oracle.rs:4-35  feas: sum_k F_k x_k > 0, cut (-sym_quad(F_k),
+                                     SingleCut(ep)).  table = F_0..F_{n-1} only; aux[0] = m                          */
+#define ELL_ORACLE_COUNT       18
 
 /* ======================================================================================= *
  *  Batched mode: `count` independent problems, the whole cutting-plane loop on-device.

@@ -428,11 +428,58 @@ struct LMI {
     }
 };
 
-// ---- tests/lmi_tests.rs:121-172 (MyLmiOracle generalised to L blocks; L=2 in the reference) -------
-struct LmiLinOpt {
+// ---- src/oracles/lmi_old_oracle.rs:5-50: forms the whole matrix A = B - sum_k F_k x_k (k outermost), then factorize ----
+struct LMIOld {
+    const double* mat_f;
+    const double* mat_b;
+    std::size_t nvar, m;
+    LDLTMgr mgr;
+    LMIOld(const double* f, const double* b, std::size_t nvar_, std::size_t m_) : mat_f(f), mat_b(b), nvar(nvar_), m(m_), mgr(m_) {}
+    FeasAnswer assess_feas(const Vec& xc) {
+        const std::size_t n = xc.size();
+        Vec a(mat_b, mat_b + m * m);                                   // :30
+        for (std::size_t k = 0; k < n; ++k) {                          // :31-40
+            const double xk = xc[k];
+            for (std::size_t i = 0; i < m; ++i)
+                for (std::size_t j = 0; j < m; ++j) a[i * m + j] = a[i * m + j] - mat_f[k * m * m + i * m + j] * xk;
+        }
+        const bool feas = mgr.factor([&](std::size_t i, std::size_t j) { return a[i * m + j]; });   // factorize, ldlt_mgr.rs:22-24
+        if (feas) return std::nullopt;
+        const double ep = mgr.witness();
+        Vec g(n);
+        for (std::size_t k = 0; k < n; ++k) g[k] = mgr.sym_quad(mat_f + k * m * m, m);
+        return CutPair{g, Cut::single(ep)};
+    }
+};
+
+// ---- src/oracles/lmi0_oracle.rs:4-35: F(x) = sum_k F_k x_k > 0 (no constant term); the reference returns (g, ep) without
+// a cut type — used as a feasibility oracle the pair becomes (g, SingleCut(ep)) like its two siblings ----
+struct LMI0 {
+    const double* mat_f;
+    std::size_t nvar, m;
+    LDLTMgr mgr;
+    LMI0(const double* f, const double* /*unused*/, std::size_t nvar_, std::size_t m_) : mat_f(f), nvar(nvar_), m(m_), mgr(m_) {}
+    FeasAnswer assess_feas(const Vec& x) {
+        const std::size_t n = x.size();
+        const bool feas = mgr.factor([&](std::size_t i, std::size_t j) {   // :18-24
+            double s = 0.0;
+            for (std::size_t k = 0; k < n; ++k) s += mat_f[k * m * m + i * m + j] * x[k];
+            return s;
+        });
+        if (feas) return std::nullopt;
+        const double ep = mgr.witness();
+        Vec g(n);
+        for (std::size_t k = 0; k < n; ++k) g[k] = -mgr.sym_quad(mat_f + k * m * m, m);   // :31
+        return CutPair{g, Cut::single(ep)};
+    }
+};
+
+// ---- tests/lmi_tests.rs:121-172 (MyLmiOracle<T> generalised to L blocks; L=2 in the reference) -------
+template <class Block>
+struct LmiLinOptT {
     int idx = -1;
     Vec c;
-    std::vector<LMI> blocks;
+    std::vector<Block> blocks;
     OptimAnswer assess_optim(const Vec& xc, double& gamma) {
         const double f0 = dot(c, xc);
         const int nc = static_cast<int>(blocks.size()) + 1;
@@ -449,6 +496,7 @@ struct LmiLinOpt {
         return {{c, Cut::single(0.0)}, true};
     }
 };
+using LmiLinOpt = LmiLinOptT<LMI>;
 
 // ---- tests/example2_tests.rs:12-48 ----------------------------------------------------------------
 struct Example2 {

@@ -63,6 +63,8 @@ def lib():
         L.ellref_ldlt.restype = C.c_int
         L.ellref_lmi_assess.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _pd]
         L.ellref_lmi_assess.restype = C.c_int
+        L.ellref_lmi_assess_variant.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _pd]
+        L.ellref_lmi_assess_variant.restype = C.c_int
         L.ellref_profit_assess.argtypes = [C.c_void_p, C.c_void_p, _pd, C.c_void_p, _pd]
         L.ellref_profit_assess.restype = C.c_int
         L.ellref_lowpass_table.argtypes = [C.c_int64, C.c_void_p]

@@ -111,15 +111,30 @@ int solve_one(const ell_batch_desc& d, const ell_batch_result& r, int64_t i) {
             break;
         }
         case ELL_ORACLE_LMI_LINOPT: {
-            LmiLinOpt o;
-            o.c.assign(d.table, d.table + n);
-            const double* t = d.table + n;
-            for (int b = 0; b < d.aux[0]; ++b) {
-                const std::size_t m = static_cast<std::size_t>(d.aux[1 + b]);
-                o.blocks.emplace_back(t, t + n * m * m, n, m);
-                t += (n + 1) * m * m;
-            }
-            optim(o);
+            auto run = [&](auto o) {
+                o.c.assign(d.table, d.table + n);
+                const double* t = d.table + n;
+                for (int b = 0; b < d.aux[0]; ++b) {
+                    const std::size_t m = static_cast<std::size_t>(d.aux[1 + b]);
+                    o.blocks.emplace_back(t, t + n * m * m, n, m);
+                    t += (n + 1) * m * m;
+                }
+                optim(o);
+            };
+            // aux[7] = 1 (checker only): the blocks are LMIOldOracle instead of LMIOracle (tests/lmi_tests.rs:208-225)
+            if (d.aux[7] == 1) run(LmiLinOptT<LMIOld>{}); else run(LmiLinOpt{});
+            break;
+        }
+        case ELL_ORACLE_LMI_OLD: {
+            const std::size_t m = static_cast<std::size_t>(d.aux[0]);
+            LMIOld o(d.table, d.table + n * m * m, n, m);
+            feas(o);
+            break;
+        }
+        case ELL_ORACLE_LMI0: {
+            const std::size_t m = static_cast<std::size_t>(d.aux[0]);
+            LMI0 o(d.table, nullptr, n, m);
+            feas(o);
             break;
         }
         default: return ELLCUDA_E_ARG;
@@ -282,15 +297,23 @@ int ellref_ldlt(int64_t n_, const double* mat, int allow_semidefinite, int64_t* 
     return spd ? 1 : 0;
 }
 
-// LMIOracle::assess_feas once; returns 1 if a cut was produced (g[n], *beta), 0 if feasible
-int ellref_lmi_assess(int64_t nvar, int64_t m, const double* f, const double* b, const double* xc, double* g, double* beta) {
-    LMI o(f, b, static_cast<std::size_t>(nvar), static_cast<std::size_t>(m));
+// {LMIOracle, LMIOldOracle, LMI0Oracle}::assess_feas once (variant 0, 1, 2; b is unused for LMI0); returns 1 if a cut was
+// produced (g[n], *beta), 0 if feasible
+int ellref_lmi_assess_variant(int variant, int64_t nvar, int64_t m, const double* f, const double* b, const double* xc, double* g,
+                              double* beta) {
     Vec x(xc, xc + nvar);
-    auto c = o.assess_feas(x);
+    FeasAnswer c;
+    const std::size_t nv = static_cast<std::size_t>(nvar), mm = static_cast<std::size_t>(m);
+    if (variant == 1) { LMIOld o(f, b, nv, mm); c = o.assess_feas(x); }
+    else if (variant == 2) { LMI0 o(f, b, nv, mm); c = o.assess_feas(x); }
+    else { LMI o(f, b, nv, mm); c = o.assess_feas(x); }
     if (!c) return 0;
     std::copy(c->first.begin(), c->first.end(), g);
     *beta = c->second.beta0;
     return 1;
+}
+int ellref_lmi_assess(int64_t nvar, int64_t m, const double* f, const double* b, const double* xc, double* g, double* beta) {
+    return ellref_lmi_assess_variant(0, nvar, m, f, b, xc, g, beta);
 }
 
 // ProfitOracle::assess_optim once on a fresh oracle (profit_oracle.rs:262-277): returns shrunk

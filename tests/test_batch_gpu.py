@@ -230,6 +230,35 @@ def test_lmi_reference_matrices(ref):  # tests/lmi_tests.rs:14-64: (F1,B1) is fe
     assert (g.has_xbest[0], g.num_iters[0], g.exit_status[0]) == (1, 0, A.EXIT_FEASIBLE)
 
 
+@pytest.mark.parametrize("n,m,count,general", [(64, 16, 64, False), (20, 7, 33, False), (12, 4, 40, True)])
+def test_lmi_old_and_lmi0_device_oracles(ref, n, m, count, general):
+    """ELL_ORACLE_LMI_OLD (src/oracles/lmi_old_oracle.rs) and ELL_ORACLE_LMI0 (lmi0_oracle.rs) on the device against the
+    checker's literal restatements (LMIOld there really forms the full matrix, k outermost)"""
+    prob = W.lmi(count, n=n, m=m, general=general, upper_scale=1e-3)
+    prob.oracle_id = A.ORACLE_LMI_OLD
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"lmi_old n={n} m={m}")
+    prob.oracle_id = A.ORACLE_LMI
+    g2 = batch.solve_batch(prob)
+    assert np.array_equal(g.num_iters, g2.num_iters) and np.array_equal(g.xc, g2.xc)      # same trajectory as LMIOracle
+    prob = W.lmi0(count, n=n, m=m)
+    if general:
+        prob.mq0 = W.lmi(count, n=n, m=m, general=True, upper_scale=1e-3).mq0
+    g, r = both(ref, prob)
+    assert_parity(g, r, exact=True, what=f"lmi0 n={n} m={m}")
+    assert len(set(g.exit_status.tolist())) >= 1 and (g.num_iters > 0).any()
+
+
+def test_lmi0_reference_matrices(ref):  # tests/lmi_tests.rs:79-113: lmi0_matrices(), feasible at (1,0,1)
+    f0 = np.array([1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0])
+    for xc0, feasible_at_start in (([1.0, 0.0, 1.0], True), ([-1.0, 0.0, -1.0], False), ([1.0, 1.0, 1.0], False)):
+        prob = BatchProblem(oracle_id=A.ORACLE_LMI0, n=3, count=2, mode=A.MODE_FEAS, kind=A.KIND_ELLSTABLE, kappa0=10.0,
+                            xc0=xc0, table=f0, aux=[2])
+        g, r = both(ref, prob)
+        assert_parity(g, r, exact=True, what=f"lmi0 2x2 from {xc0}")
+        assert (g.num_iters[0] == 0 and g.exit_status[0] == A.EXIT_FEASIBLE) == feasible_at_start
+
+
 @pytest.mark.parametrize("n,m,count", [(64, 16, 96), (20, 7, 40), (33, 16, 17), (64, 5, 33)])
 def test_lmi_diagonal_start(ref, n, m, count):  # C4a: EllStable::new_with_scalar — the matrix stays diagonal
     prob = W.lmi(count, n=n, m=m)

@@ -149,6 +149,41 @@ def test_lmi_tests(ref):  # tests/lmi_tests.rs:174-225 (bounds <300 / <400; surv
     assert ref.lib().ellref_lmi_assess(3, 2, f1.ctypes.data, b1.ctypes.data, np.zeros(3).ctypes.data, g.ctypes.data, C.byref(beta)) == 0
 
 
+def _lmi_assess(ref, variant, f, b, x, m):
+    f = np.ascontiguousarray(f, dtype=float)
+    b = np.ascontiguousarray(b if b is not None else np.zeros(m * m), dtype=float)
+    x = np.ascontiguousarray(x, dtype=float)
+    g, beta = np.zeros(len(x)), C.c_double()
+    cut = ref.lib().ellref_lmi_assess_variant(variant, len(x), m, f.ctypes.data, b.ctypes.data, x.ctypes.data, g.ctypes.data, C.byref(beta))
+    return cut, g, beta.value
+
+
+def test_lmi_old_and_lmi0_oracles(ref):
+    """src/oracles/lmi_old_oracle.rs, lmi0_oracle.rs — tests/lmi_tests.rs:66-113 (LMI0 direct calls), :208-225 (LMIOld in
+    MyLmiOracle under Ell and EllStable: < 300 / < 400)"""
+    f1 = LMI_TAB[3:15]
+    assert _lmi_assess(ref, 2, f1, None, np.zeros(3), 2)[0] == 1                     # test_lmi0_oracle: cut.is_some()
+    f0 = [1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0]               # lmi0_matrices()
+    assert _lmi_assess(ref, 2, f0, None, [1.0, 0.0, 1.0], 2)[0] == 0                 # feasible
+    cut, g, ep = _lmi_assess(ref, 2, f0, None, [-1.0, 0.0, -1.0], 2)                 # infeasible: g = (-1, -0, -0), ep = 1
+    assert cut == 1 and g[0] == -1.0 and g[1] == 0.0 and g[2] == 0.0 and ep == 1.0
+    assert np.signbit(g[1]) and np.signbit(g[2])                                     # the reference negates sym_quad: -0.0
+    assert _lmi_assess(ref, 2, f0, None, [1.0, 1.0, 1.0], 2)[0] == 1                 # infeasible2
+    # LMIOld: same element arithmetic as LMIOracle => the same trajectory, not merely < 300 / < 400
+    for kind, bound, exact, gam in ((A.KIND_ELL, 300, 11, -3.7502205782089257), (A.KIND_ELLSTABLE, 400, 21, -3.5724046875091333)):
+        o = one(ref, oracle_id=A.ORACLE_LMI_LINOPT, n=3, kind=kind, kappa0=10.0, gamma0=math.inf, table=LMI_TAB, aux=[2, 2, 3, 0, 0, 0, 0, 1])
+        assert o.has_xbest[0] == 1 and o.num_iters[0] < bound and o.num_iters[0] == exact and o.gamma[0] == gam
+    # as plain feasibility oracles on a random instance: LMIOld == LMI bit for bit; LMI0 runs
+    p = W.lmi(6, n=12, m=4)
+    a = ref.solve(p)
+    p.oracle_id = A.ORACLE_LMI_OLD
+    b = ref.solve(p)
+    assert np.array_equal(a.num_iters, b.num_iters) and np.array_equal(a.xc, b.xc) and np.array_equal(a.exit_status, b.exit_status)
+    o = ref.solve(W.lmi0(6, n=12, m=4))
+    assert set(o.exit_status.tolist()) <= {A.EXIT_FEASIBLE, A.EXIT_NOSOLN, A.EXIT_TOL, A.EXIT_MAXIT}
+    assert (o.exit_status == A.EXIT_FEASIBLE).any()
+
+
 def test_lowpass(ref):  # src/oracles/lowpass_oracle.rs:153-194 literal case is degenerate (SURVEY §0.5)
     t = ref.lowpass_table(32)
     p = W.lowpass(1, t)
