@@ -12,6 +12,14 @@ def _lowpass(R):
     return W.lowpass(3, R.lowpass_table(32) if hasattr(R, "lowpass_table") else R, max_iters=50000)
 
 
+def _lowpass_bands(R):
+    """awkward band layouts (short bands, empty transition band, edges on multiples of 32): the TMEM kernel's rounds"""
+    p = W.lowpass(5, R.lowpass_table(32) if hasattr(R, "lowpass_table") else R, max_iters=1500)
+    for i, (wp, ws) in enumerate([(0.001, 0.002), (0.12, 0.12), (31.5 / 479, 63.5 / 479), (0.05, 0.995), (0.90, 0.9979)]):
+        p.params[i, 0], p.params[i, 1] = wp, ws
+    return p
+
+
 CASES = {
     "example1": lambda R: W.example1(),
     "profit": lambda R: W.profit(64),
@@ -24,6 +32,9 @@ CASES = {
     "lowpass32": _lowpass,
     "lmi_diag": lambda R: W.lmi(6, n=64, m=16),
     "lmi_general": lambda R: W.lmi(6, n=64, m=16, general=True, upper_scale=1e-6),
+    "lmi_old": lambda R: (lambda p: (setattr(p, "oracle_id", A.ORACLE_LMI_OLD), p)[1])(W.lmi(4, n=20, m=7)),
+    "lmi0": lambda R: W.lmi0(6, n=64, m=16),
+    "lowpass32_bands": lambda R: _lowpass_bands(R),
 }
 
 
