@@ -1,18 +1,22 @@
 // batch_lowpass.cu — the headline path (LowpassOracle, n = 32, cutting_plane_optim on Ell): one warp per problem,
-// persistent, with TENSOR MEMORY as a second operand store next to shared memory.
+// persistent, with M held in TENSOR MEMORY instead of registers.
 //
 // Why: the generic warp-per-problem kernel (batch_warp.cu) runs this workload at 88 % of the shared-memory data pipe
-// (profiles/r01c_*): per iteration it moves ~595 shared-memory wavefronts, 314 for spectrum rows, 140 for re-reading
-// the broadcast copy of x every 32-row round, 141 for the update.  FP64 issue sits at 43 %.  Tensor memory is a
-// separate datapath (tools/ubench_tmem.cu: 410 B/clk/SM next to shared memory's 128 B/clk/SM), so:
-//   * M lives in TMEM between updates (lane i = row i, 64 columns per warp), not in registers;
-//   * that frees 64 registers during the oracle phase for x (read once per oracle call instead of once per round);
-//   * the last 8 of the 32 columns of every spectrum row come from TMEM, the first 24 from shared memory;
-// TMEM is lane-addressed: thread L of a warp reaches only lane 32*(warp%4)+L, at a warp-uniform column.  Spectrum row r
-// is therefore stored in lane r%32, column block r/32, and a round of 32 consecutive rows k0..k0+31 is evaluated with
-// thread L on the row whose index is congruent to L (traversal position p = (L - k0) mod 32).  The rows of a round
-// straddle at most two column blocks: both are loaded and each thread keeps its own.  A round never crosses the
-// band's wrap-around point.  "First violated row in traversal order" is the lowest set bit of the ballot rotated by k0.
+// (profiles/r01c_prof_batch3_*): per iteration it moves ~595 shared-memory wavefronts — 314 for spectrum rows (36 of them
+// bank conflicts where a round wraps around the band), 140 for re-reading the broadcast copy of x every 32-row round,
+// 141 for the update — while its registers are full (M's row = 64 of 128).  Tensor memory is a separate datapath
+// (tools/ubench_tmem.cu: 410 B/clk/SM next to shared memory's 128 B/clk/SM), so:
+//   * M lives in TMEM between updates (TMEM lane 32*(warp%4)+i = row i, 64 columns per warp; tcgen05.ld before M.g,
+//     tcgen05.st after the rank-1 update);
+//   * that frees 64 registers during the oracle phase for x, read once per oracle call instead of once per round;
+//   * a round of 32 consecutive rows k0..k0+31 is evaluated with thread L on the row congruent to L mod 32 (traversal
+//     position p = (L - k0) mod 32); a round never crosses the band's wrap-around point, so the rows of a half-warp always
+//     sit in distinct banks.  "First violated row in traversal order" = lowest set bit of the ballot rotated by k0.
+// 470 wavefronts per iteration, 503 M iter/s against 445 (profiles/r01c_prof_batch5_*).
+// Experimental variants (ELLCUDA_LOWPASS_VARIANT) additionally read the last 8 columns of every spectrum row from TMEM:
+// row r is stored in lane r%32, column block r/32 (TMEM is lane-addressed at a warp-uniform column); a window straddles
+// two blocks, both are loaded and each thread keeps its own (variant 1), or rounds are aligned to blocks (variant 2).
+// Fewer wavefronts (396) but more instructions or rounds: 490 / 482 M iter/s, so they are not the default.
 //
 // Arithmetic and its order are those of batch_warp.cu (= the reference's): every row dot is summed left to right
 // over j = 0..31, M.g likewise, omega sequentially over k; compiled -fmad=false.
@@ -26,7 +30,6 @@ namespace {
 
 constexpr int kN = 32;
 constexpr int kTabStride = 33;          // doubles per shared-memory row (odd: rows of one half-warp hit distinct banks)
-constexpr int kTmemCols = 512;
 constexpr int kMCols = 64;              // one M row per lane: 32 doubles
 constexpr int kTabCol0 = 4 * kMCols;    // 4 warps per lane quarter keep their M in columns [0, 256)
 constexpr int kTabBlkCols = 16;         // 32-bit columns per 32-row block of the spectrum tail (8 doubles per row)
