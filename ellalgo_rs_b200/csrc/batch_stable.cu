@@ -61,10 +61,13 @@ struct LmiShared {
 __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, double& g0, double& g1, double& ep) {
     const int m = L.m, tri = L.tri, n = L.nvar;
     // --- elements A(i,j) = B[i][j] - sum_k F_k[i][j]*x[k], k ascending (src/oracles/lmi_oracle.rs:28-34)
-    for (int e0 = lane; e0 < tri; e0 += 32 * 4) {
-        double a[4];
+    // 5 elements per lane per pass: m = 16 (136 elements) is one pass with every lane busy (4 per lane needed a second
+    // pass with 8 active lanes: -900 instructions per call)
+    constexpr int U = 5;
+    for (int e0 = lane; e0 < tri; e0 += 32 * U) {
+        double a[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int e = e0 + 32 * u;
             a[u] = (e < tri && !L.lmi0) ? L.bp[e] : 0.0;
         }
@@ -73,7 +76,7 @@ __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, doub
                 const double xk = wm.sx[k];
                 const double* fk = L.fp + k * L.fstride;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int e = e0 + 32 * u;
                     if (e < tri) a[u] -= fk[e] * xk;
                 }
@@ -83,14 +86,14 @@ __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, doub
                 const double xk = wm.sx[k];
                 const double* fk = L.fp + k * L.fstride;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int e = e0 + 32 * u;
                     if (e < tri) a[u] += fk[e] * xk;
                 }
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int e = e0 + 32 * u;
             if (e < tri) wm.sa[e] = a[u];
         }
