@@ -96,3 +96,51 @@ def test_fuzz_small_oracles(ref, seed):  # batch_small_kernel: profit family, bo
         prob.xc0 = rng.uniform(-2.0, 6.0, (count, 2))
     exact = True   # exp/ln on the device are glibc's (csrc/glibc_math.cuh)
     assert_parity(batch.solve_batch(prob), ref.solve(prob), exact=exact, what=f"profit fuzz seed={seed} count={count}")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_single_ellipsoid_trajectory(ref, seed):
+    """ellcuda_update on a handle (sweep + finish kernels, deferred rank-1): random n (tile-unaligned), random start, a random
+    walk over update kinds and cut depths that mixes Success / NoSoln / NoEffect, a clone and a set_xc in the middle —
+    status, tsq, kappa, xc after every step and the full matrix at the end, bit for bit"""
+    from ellalgo_rs_b200.cutting_plane import ParallelCut, SingleCut
+    from ellalgo_rs_b200.ell import Ell
+
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.choice([1, 2, 3, 31, 63, 64, 65, 127, 129, 200, 333, 511, 700])) if seed else 1
+    xc = rng.uniform(-1, 1, n)
+    no_defer = bool(rng.integers(0, 2))
+    use_par = bool(rng.integers(0, 2))
+    kw = {}
+    if seed % 3 == 1:
+        kw["diag"] = rng.uniform(0.5, 2.0, n)
+    elif seed % 3 == 2:
+        a = rng.uniform(-1, 1, (n, n)) / n
+        kw["mq"] = np.eye(n) + a + a.T
+    kappa = 1.0 if kw else float(rng.uniform(0.5, 5.0))
+    e = Ell(kappa, xc, no_defer_trick=no_defer, use_parallel_cut=use_par, **kw)
+    s = ref.Space(A.KIND_ELL, n, kappa=kappa, xc=xc, no_defer_trick=no_defer, use_parallel_cut=use_par, **kw)
+    for k in range(14):
+        g = rng.uniform(-1, 1, n) / math.sqrt(n)
+        tau = math.sqrt(max(s.state()["tsq"], 1e-3)) if k else 1.0
+        which = int(rng.integers(0, 3))
+        b0 = float(rng.choice([-0.5, 0.0, 0.05, 0.3, 0.9, 1.5]) * tau)
+        if rng.integers(0, 2):
+            cut = SingleCut(b0)
+            st_r = s.update(which, g, b0)
+        else:
+            b1 = None if rng.integers(0, 4) == 0 else float(b0 + rng.choice([-0.1, 0.05, 0.4, 2.0]) * tau)
+            cut = ParallelCut(b0, b1)
+            st_r = s.update(which, g, b0, b1, single=False)
+        st_g = [e.update_bias_cut, e.update_central_cut, e.update_q][which]((g, cut))
+        r = s.state()
+        assert int(st_g) == st_r, f"seed {seed} n {n} step {k}: status {int(st_g)} vs {st_r}"
+        same = lambda a, b: np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)   # n = 1: cst1 = 1/0, NaNs as in the reference
+        assert same(e.tsq(), r["tsq"]) and same(e.kappa, r["kappa"]), f"seed {seed} n {n} step {k}: tsq/kappa"
+        assert same(e.xc(), r["xc"]), f"seed {seed} n {n} step {k}: xc"
+        if k == 6:
+            e = e.clone()                      # the pending rank-1 must travel with the copy
+            x2 = rng.uniform(-1, 1, n)
+            e.set_xc(x2)
+            s.set_xc(x2)
+    assert np.array_equal(e.mq, s.state()["mq"], equal_nan=True), f"seed {seed} n {n}: final matrix"
