@@ -119,8 +119,11 @@ class Space:
                                          int(no_defer_trick), int(use_parallel_cut))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().ellref_space_free(self._h)
+        if getattr(self, "_h", None) and lib is not None:     # module globals are already None at interpreter shutdown
+            try:
+                lib().ellref_space_free(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def clone(self):
