@@ -65,6 +65,12 @@ def lib():
         L.ellref_lmi_assess.restype = C.c_int
         L.ellref_lmi_assess_variant.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _pd]
         L.ellref_lmi_assess_variant.restype = C.c_int
+        L.ellref_dot.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.ellref_dot.restype = C.c_double
+        L.ellref_dot_mv.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        L.ellref_dot_mv.restype = None
+        L.ellref_linspace.argtypes = [C.c_double, C.c_double, C.c_int64, C.c_void_p]
+        L.ellref_linspace.restype = None
         L.ellref_profit_assess.argtypes = [C.c_void_p, C.c_void_p, _pd, C.c_void_p, _pd]
         L.ellref_profit_assess.restype = C.c_int
         L.ellref_lowpass_table.argtypes = [C.c_int64, C.c_void_p]

@@ -358,6 +358,15 @@ void ellref_lowpass_table(int64_t n, double* out) {
     const Vec s = lowpass_spectrum(static_cast<std::size_t>(n));
     std::copy(s.begin(), s.end(), out);
 }
+// Arr::dot (arr.rs:443-451), Arr::dot_mv (:426-442), linspace (:506-520) on their own (arr.rs:676-709 known answers)
+double ellref_dot(const double* a, const double* b, int64_t n) { return dot(a, b, static_cast<std::size_t>(n)); }
+void ellref_dot_mv(const double* m, const double* x, int64_t rows, int64_t cols, double* out) {
+    dot_mv(m, x, static_cast<std::size_t>(rows), static_cast<std::size_t>(cols), out);
+}
+void ellref_linspace(double start, double end, int64_t n, double* out) {
+    const Vec v = linspace(start, end, static_cast<std::size_t>(n));
+    std::copy(v.begin(), v.end(), out);
+}
 int ellref_lowpass_band_edge(int64_t n, double w) { return lowpass_band_edge(static_cast<std::size_t>(n), w); }
 void ellref_lowpass_case_params(double* out5) { lowpass_case_params(out5); }
 

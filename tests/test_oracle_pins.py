@@ -230,6 +230,46 @@ def test_ell_calc(ref):  # src/ell_calc.rs:971-1046, 1120-1186
     assert ref.calc(4, 2, 0.07, 0.03, tsq=0.01)[0] == A.NOSOLN  # calc_parallel_q beta1 < beta0
 
 
+def test_arr_ops_on_the_path(ref):  # src/arr.rs:676-709: dot_mv, dot, linspace known answers
+    L = ref.lib()
+    m, v, y = np.eye(3), np.array([2.0, 3.0, 4.0]), np.zeros(3)
+    L.ellref_dot_mv(m.ctypes.data, v.ctypes.data, 3, 3, y.ctypes.data)
+    assert y[0] == 2.0 and np.array_equal(y, v)
+    a, b = np.array([1.0, 2.0, 3.0]), np.array([4.0, 5.0, 6.0])
+    assert L.ellref_dot(a.ctypes.data, b.ctypes.data, 3) == 32.0
+    out = np.zeros(5)
+    L.ellref_linspace(0.0, 10.0, 5, out.ctypes.data)
+    assert out[2] == 5.0 and out[0] == 0.0 and out[4] == 10.0
+    # sequential, separately rounded: 1e16 + 1 + 1 stays 1e16 left to right (a pairwise or fused sum would not)
+    a, b = np.array([1e16, 1.0, 1.0, -1e16]), np.ones(4)
+    assert L.ellref_dot(a.ctypes.data, b.ctypes.data, 4) == 0.0
+
+
+def test_ell_calc_additional_tests(ref):  # src/ell_calc_additional_tests.rs:6-88 — exact assert_eq! on (rho, sigma, delta)
+    assert ref.calc(4, 1, tsq=0.0) == (A.SUCCESS, (0.0, 0.4, 16.0 / 15.0))                      # central cut, tsq = 0
+    st, v = ref.calc(4, 1, tsq=0.01)
+    assert st == A.SUCCESS and min(v) > 0.0
+    assert ref.calc(4, 1, 0.0, 0.0, tsq=0.0) == (A.SUCCESS, (0.0, 0.4, 16.0 / 15.0))            # parallel central (0, 0)
+    st, v = ref.calc(4, 1, 0.0, 0.05, tsq=0.01)
+    assert st == A.SUCCESS and min(v) > 0.0
+    assert ref.calc(4, 1, 0.0, -0.1, tsq=0.01) == (A.NOSOLN, (0.0, 0.0, 0.0))
+    st, v = ref.calc(4, 1, 0.0, 0.1, tsq=0.2)
+    assert st == A.SUCCESS and min(v) > 0.0
+    assert ref.calc(4, 1, 0.0, -0.1, tsq=0.2) == (A.NOSOLN, (0.0, 0.0, 0.0))
+
+
+def test_ell_construct_and_accessors(ref):  # src/ell_test.rs:12-20, 131-155
+    s = ref.Space(A.KIND_ELL, 4, kappa=0.01)
+    st = s.state()
+    assert st["kappa"] == 0.01 and st["tsq"] == 0.0 and np.array_equal(st["mq"], np.eye(4)) and np.array_equal(st["xc"], np.zeros(4))
+    s = ref.Space(A.KIND_ELL, 3, kappa=1.0, diag=np.array([1.0, 2.0, 3.0]))
+    st = s.state()
+    assert st["kappa"] == 1.0 and np.array_equal(st["mq"], np.diag([1.0, 2.0, 3.0])) and st["tsq"] == 0.0
+    s = ref.Space(A.KIND_ELL, 2, kappa=1.0)
+    s.set_xc(np.array([1.0, 2.0]))
+    assert np.array_equal(s.state()["xc"], [1.0, 2.0]) and s.state()["tsq"] == 0.0
+
+
 # ---------------------------------------------------------------- §4(a): Ell / EllStable single steps
 @pytest.mark.parametrize("kind", [A.KIND_ELL, A.KIND_ELLSTABLE])
 def test_space_single_steps(ref, kind):  # src/ell.rs:246-314, src/ell_stable.rs:225-298

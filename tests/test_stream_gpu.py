@@ -53,6 +53,16 @@ def test_ell_known_answers():
     assert e.kappa == 1.0
 
 
+def test_ell_construct_and_accessors():  # src/ell_test.rs:12-20, 131-155 on the GPU search space
+    e = Ell.new_with_scalar(0.01, np.zeros(4))
+    assert e.kappa == 0.01 and e.tsq() == 0.0 and np.array_equal(e.mq, np.eye(4)) and np.array_equal(e.xc(), np.zeros(4))
+    e = Ell(1.0, np.zeros(3), diag=np.array([1.0, 2.0, 3.0]))            # Ell::new(val, xc)
+    assert e.kappa == 1.0 and np.array_equal(e.mq, np.diag([1.0, 2.0, 3.0])) and e.tsq() == 0.0
+    e = Ell.new_with_scalar(1.0, np.zeros(2))
+    e.set_xc(np.array([1.0, 2.0]))
+    assert np.array_equal(e.xc(), [1.0, 2.0]) and e.tsq() == 0.0
+
+
 # ---------------------------------------------------------------- stepwise trajectories against the checker
 def _cuts(n, steps, seed):
     rng = np.random.default_rng(seed)
