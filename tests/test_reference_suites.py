@@ -2,7 +2,7 @@
 search space (`ellalgo_rs_b200.ell.Ell`, i.e. libellcuda.so behind the SearchSpace surface), with the reference's asserts:
 
     tests/regression_tests.rs        tests/numerical_stability.rs     tests/integration_test.rs
-    tests/quasicvx2_tests.rs         tests/stress_tests.rs
+    tests/quasicvx2_tests.rs         tests/stress_tests.rs            tests/cutting_plane_tests.rs:328-379 (BSearchAdaptor)
 
 The oracles are user code in the reference (closures over `Arr`), so here they are host-side Python objects — the drop-in
 story of INTEGRATION.md §1: user oracle on the host, ellipsoid on the device.  Every arithmetic expression keeps the
@@ -15,7 +15,8 @@ import numpy as np
 import pytest
 
 from ellalgo_rs_b200 import _abi as A
-from ellalgo_rs_b200.cutting_plane import CutStatus, Options, ParallelCut, SingleCut, cutting_plane_optim
+from ellalgo_rs_b200.cutting_plane import (BSearchAdaptor, CutStatus, Options, ParallelCut, SingleCut, bsearch,
+                                           cutting_plane_optim)
 
 INF = math.inf
 SPACES = ["checker", pytest.param("gpu", marks=pytest.mark.gpu)]
@@ -24,8 +25,14 @@ SPACES = ["checker", pytest.param("gpu", marks=pytest.mark.gpu)]
 class CheckerSpace:
     """SearchSpace surface (src/cutting_plane.rs:154-182) over the CPU checker's Ell"""
 
-    def __init__(self, ref, kappa, xc):
-        self.s = ref.Space(A.KIND_ELL, len(xc), kappa=kappa, xc=np.asarray(xc, dtype=np.float64))
+    def __init__(self, ref, kappa, xc, _space=None):
+        self.s = _space if _space is not None else ref.Space(A.KIND_ELL, len(xc), kappa=kappa, xc=np.asarray(xc, dtype=np.float64))
+
+    def clone(self):
+        return CheckerSpace(None, None, None, _space=self.s.clone())
+
+    def set_xc(self, x):
+        self.s.set_xc(np.asarray(x, dtype=np.float64))
 
     def xc(self):
         return self.s.state()["xc"].copy()
@@ -294,3 +301,29 @@ def test_stress_suite(ref, kind):
     sane = [0.12, 0.20, (1.0 / 1.025) ** 2, 1.025 ** 2, 0.125 ** 2]
     x, niter, gamma = solve(kind, ref, lambda: LowpassHost(ref, 32, sane), 40.0, [0.0] * 32, sane[4], Options(150, 1e-14))
     assert niter == 150 and gamma <= sane[4]
+
+
+# ------------------------------------------------------------------------------------------------ cutting_plane_tests.rs:328-379
+class MyOracleFeas2:  # feasible when x + y <= 3; OracleFeas::update is the default no-op (src/cutting_plane.rs:125)
+    def assess_feas(self, xc):
+        fj = xc[0] + xc[1] - 3.0
+        if fj > 0.0:
+            return np.array([1.0, 1.0]), SingleCut(fj)
+        return None
+
+    def update(self, gamma):
+        pass
+
+
+@pytest.mark.parametrize("kind", SPACES)
+def test_bsearch_adaptor_suite(ref, kind):
+    def run(k):
+        adaptor = BSearchAdaptor(MyOracleFeas2(), make_space(k, ref, 10.0, [0.0, 0.0]), Options())
+        assert np.array_equal(adaptor.space.xc(), [0.0, 0.0])                                          # :370-379
+        feasible, niter = bsearch(adaptor, (-100.0, 100.0), Options(2000, 1e-8))                       # :358-368
+        return feasible, niter, adaptor.space.xc()
+    feasible, niter, x = run(kind)
+    assert feasible
+    if kind == "gpu":
+        f2, n2, x2 = run("checker")
+        assert (feasible, niter) == (f2, n2) and np.array_equal(x, x2)
