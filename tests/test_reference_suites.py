@@ -327,3 +327,77 @@ def test_bsearch_adaptor_suite(ref, kind):
     if kind == "gpu":
         f2, n2, x2 = run("checker")
         assert (feasible, niter) == (f2, n2) and np.array_equal(x, x2)
+
+
+# ------------------------------------------------------------------------------------------------ benches/ellipsoid.rs
+class BenchOracle:  # benches/ellipsoid.rs:10-24: gradient = 2*xc, f = xc.dot(xc)
+    def assess_optim(self, xc, gamma):
+        grad = 2.0 * xc
+        f = 0.0
+        for v in xc:
+            f += v * v
+        if f < gamma:
+            return (grad, SingleCut(f)), True, f
+        return (grad, SingleCut(f)), False, gamma
+
+
+@pytest.mark.parametrize("kind", SPACES)
+def test_reference_criterion_bench_configuration(ref, kind):
+    """the reference's own benchmark (dimensions 10 / 50 / 100, Ell::new_with_scalar(10, 0), gamma = -inf, default Options)
+    starts at the minimiser with a zero gradient: omega = 0, a 0/0 in the cut formulas, Success with NaN state, and the
+    loop ends at iteration 0 on tsq < tol — the same on both spaces"""
+    for dim in (10, 50, 100):                                                                          # :29-44
+        x, niter, gamma = solve(kind, ref, BenchOracle, 10.0, [0.0] * dim, -INF, Options())
+        assert x is None and niter == 0 and gamma == -INF
+
+
+# ------------------------------------------------------------------------------------------------ examples/quickcheck_tests.rs
+@pytest.mark.parametrize("kind", SPACES)
+def test_quickcheck_properties(ref, kind):
+    """the reference's property tests (examples/quickcheck_tests.rs:62-262) with its generators (n = 1..4, kappa = |v| % 10 +
+    0.001), 100 seeded draws per property, on both spaces; on the GPU every draw must also reproduce the checker's status,
+    kappa and tsq exactly"""
+    rng = np.random.default_rng(20240)
+
+    def draw():
+        return int(rng.integers(1, 5)), float(abs(rng.normal(0.0, 50.0)) % 10.0 + 0.001)
+
+    def step(n, kappa, update, grad, cut):
+        spaces = [make_space(kind, ref, kappa, np.zeros(n))] + ([CheckerSpace(ref, kappa, np.zeros(n))] if kind == "gpu" else [])
+        res = []
+        for sp in spaces:
+            st = getattr(sp, update)((np.full(n, grad), cut))
+            kap = sp.kappa if hasattr(sp, "kappa") else sp.s.state()["kappa"]
+            res.append((int(st), float(kap), float(sp.tsq())))
+        if kind == "gpu":
+            assert res[0][0] == res[1][0] and np.array_equal(res[0][1:], res[1][1:], equal_nan=True), res
+        return res[0]
+
+    for _ in range(100):
+        n, kappa = draw()
+        st, kap, _ = step(n, kappa, "update_central_cut", 0.01, SingleCut(0.0))              # :74-86
+        assert st != CutStatus.Success or kap > 0.0
+        n, kappa = draw()
+        tsq = kappa * (n * 0.01 * 0.01)                                                        # M = I
+        st, kap, _ = step(n, kappa, "update_bias_cut", 0.01, SingleCut(abs(math.sqrt(tsq) * 0.5)))   # :88-104
+        assert st != CutStatus.Success or kap > 0.0
+        n, kappa = draw()
+        _, kap, _ = step(n, kappa, "update_central_cut", 0.1, SingleCut(0.0))                # :106-114
+        assert kap > 0.0
+        n, kappa = draw()
+        st, kap, _ = step(n, kappa, "update_central_cut", 0.01, ParallelCut(0.0, 0.05))      # :163-175
+        assert st != CutStatus.Success or kap > 0.0
+        n, kappa = draw()
+        g = np.full(n, 0.1)
+        tsq = kappa * float(sum(v * v for v in g))
+        st, _, _ = step(n, kappa, "update_bias_cut", 0.1, SingleCut(math.sqrt(tsq) * 1.5))   # :177-188
+        assert st in (CutStatus.NoEffect, CutStatus.NoSoln)
+    sp = make_space(kind, ref, 1.0, np.zeros(4))                                               # :190-201
+    for _ in range(5):
+        st = sp.update_central_cut((np.full(4, 0.1), SingleCut(0.0)))
+        kap = sp.kappa if hasattr(sp, "kappa") else sp.s.state()["kappa"]
+        assert st != CutStatus.Success or kap > 0.0
+    for n in range(1, 9):                                                                       # :132-161 (EllCalc level)
+        assert min(ref.calc(n, 1, tsq=0.1)[1]) > 0.0
+        assert min(ref.calc(n, 0, 0.5, tsq=1.0)[1]) > 0.0
+        assert min(ref.calc(n, 0, 0.3, 0.6, tsq=1.0)[1]) > 0.0
