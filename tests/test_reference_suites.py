@@ -401,3 +401,46 @@ def test_quickcheck_properties(ref, kind):
         assert min(ref.calc(n, 1, tsq=0.1)[1]) > 0.0
         assert min(ref.calc(n, 0, 0.5, tsq=1.0)[1]) > 0.0
         assert min(ref.calc(n, 0, 0.3, 0.6, tsq=1.0)[1]) > 0.0
+
+
+# ------------------------------------------------------------------------------------------------ examples/portfolio_optimization.rs
+class PortfolioOracle:  # :24-74
+    def __init__(self, expected_returns, risk_matrix, max_risk, budget):
+        self.r, self.q, self.max_risk, self.budget = np.asarray(expected_returns, float), np.asarray(risk_matrix, float), max_risk, budget
+
+    def assess_optim(self, xc, gamma):
+        n = len(xc)
+        grad = np.zeros(n)
+        viol = 0.0
+        for i in range(n):
+            viol += xc[i]
+        viol -= self.budget
+        if viol > 0.0:
+            grad[:] = 1.0
+            return (grad, SingleCut(viol)), False, gamma
+        risk = 0.0
+        for i in range(n):
+            for j in range(n):
+                risk += xc[i] * self.q[i, j] * xc[j]
+        rv = risk - self.max_risk
+        if rv > 0.0:
+            for i in range(n):
+                s = 0.0
+                for j in range(n):
+                    s += (self.q[i, j] + self.q[j, i]) * xc[j]
+                grad[i] = s
+            return (grad, SingleCut(rv)), False, gamma
+        ret = 0.0
+        for a, b in zip(self.r, xc):
+            ret += a * b
+        obj = -ret
+        if obj < gamma:
+            return (-self.r, SingleCut(0.0)), True, obj
+        return (grad, SingleCut(0.0)), False, gamma   # zero gradient: omega = 0, the cut formulas see 0/0 (as in the reference)
+
+
+@pytest.mark.parametrize("kind", SPACES)
+def test_portfolio_example(ref, kind):  # :76-95: 4 assets, identity risk, Options::new(1000, 1e-8); no asserts in the reference
+    make = lambda: PortfolioOracle([0.08, 0.12, 0.10, 0.06], np.eye(4), 0.02, 1.0)
+    x, niter, gamma = solve(kind, ref, make, 1.0, [0.0] * 4, INF, Options(1000, 1e-8))
+    assert x is not None and niter <= 1000 and gamma <= 0.0
