@@ -15,6 +15,26 @@ pub const ELL_UPDATE_Q: i32 = 2;
 pub const ELL_MODE_OPTIM: i32 = 0;
 pub const ELL_MODE_FEAS: i32 = 1;
 pub const ELL_MODE_OPTIM_Q: i32 = 2;
+pub const ELL_MODE_BSEARCH: i32 = 3;
+// built-in device oracles (include/ellcuda.h cites the reference file of each)
+pub const ELL_ORACLE_EXAMPLE1: i32 = 0;
+pub const ELL_ORACLE_EXAMPLE1_RR: i32 = 1;
+pub const ELL_ORACLE_EXAMPLE4: i32 = 2;
+pub const ELL_ORACLE_QUASICVX: i32 = 3;
+pub const ELL_ORACLE_PROFIT: i32 = 4;
+pub const ELL_ORACLE_PROFIT_RB: i32 = 5;
+pub const ELL_ORACLE_PROFIT_Q: i32 = 6;
+pub const ELL_ORACLE_LOWPASS: i32 = 7;
+pub const ELL_ORACLE_BOWL: i32 = 8;
+pub const ELL_ORACLE_LMI: i32 = 9;
+pub const ELL_ORACLE_EXAMPLE2: i32 = 10;
+pub const ELL_ORACLE_EXAMPLE3: i32 = 11;
+pub const ELL_ORACLE_HALFPLANE: i32 = 12;
+pub const ELL_ORACLE_ALWAYS_CUT: i32 = 13;
+pub const ELL_ORACLE_OPTIM_BOX: i32 = 14;
+pub const ELL_ORACLE_LMI_LINOPT: i32 = 15;
+pub const ELL_ORACLE_LMI_OLD: i32 = 16;
+pub const ELL_ORACLE_LMI0: i32 = 17;
 
 #[repr(C)]
 pub struct ellcuda_ctx {
