@@ -560,7 +560,7 @@ constexpr size_t sweep_smem(int cols, int rows, int stages) { return (size_t)sta
 
 // =================================================================================================== handle
 struct ellcuda_ctx {
-    int kind = ELL_KIND_ELL;    // ELL_KIND_ELLSTABLE handles (n <= 64) use only the `st_*` members, xc, gstage, status_host
+    int kind = ELL_KIND_ELL;    // ELL_KIND_ELLSTABLE handles (n <= 2048) use only the `st_*` members, xc, gstage, status_host
     double* st_qu = nullptr;    // EllStable: packed upper triangle incl. diagonal, n(n+1)/2
     double* st_scal = nullptr;  // EllStable: {kappa, tsq}
     int* st_status = nullptr;   // EllStable: CutStatus of the last update
@@ -739,9 +739,9 @@ int flush_pending(ellcuda_ctx* h) {  // make S hold the reference's `mq` exactly
 using namespace ellcuda;
 
 extern "C" {
-// ---- EllStable as a single host-driven search space (src/ell_stable.rs:9-35, 128-210), n <= 64 -------------------------
+// ---- EllStable as a single host-driven search space (src/ell_stable.rs:9-35, 128-210), n <= 2048 -----------------------
 static int create_stable(const ell_create_desc* d, ell_handle* out) {
-    if (d->n > 64) { set_error("a single EllStable handle supports n <= 64 (its recurrences do not stream; use batched mode)"); return ELLCUDA_E_ARG; }
+    if (d->n > 2048) { set_error("a single EllStable handle supports n <= 2048 (its recurrences are serial; the throughput path is batched mode)"); return ELLCUDA_E_ARG; }
     if ((d->row_begin != 0 || (d->row_end != 0 && d->row_end != d->n))) { set_error("EllStable does not shard"); return ELLCUDA_E_ARG; }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {

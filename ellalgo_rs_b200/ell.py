@@ -216,7 +216,7 @@ class Ell:
 
 
 class EllStable(Ell):
-    """Host mirror of the reference's `EllStable` (src/ell_stable.rs) as a single host-driven search space, n <= 64:
+    """Host mirror of the reference's `EllStable` (src/ell_stable.rs) as a single host-driven search space, n <= 2048:
     `new`, `new_with_scalar`, `new_with_matrix` (:18-35) and the SearchSpace methods (:128-166); update_core (:52-125)
     runs as one single-warp kernel per call.  `mq` returns the factor (diagonal + strict upper triangle)."""
     KIND = _abi.KIND_ELLSTABLE

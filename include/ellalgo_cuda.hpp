@@ -67,7 +67,7 @@ struct EllConfig {
 };
 
 // The reference's `Ell` (KIND = ELL_KIND_ELL, src/ell.rs) with its matrix in B200 HBM, or `EllStable`
-// (KIND = ELL_KIND_ELLSTABLE, src/ell_stable.rs, n <= 64).  Copying clones the device state (#[derive(Clone)]).
+// (KIND = ELL_KIND_ELLSTABLE, src/ell_stable.rs, n <= 2048).  Copying clones the device state (#[derive(Clone)]).
 template <int KIND>
 class EllCudaT {
   public:

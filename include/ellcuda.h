@@ -182,10 +182,11 @@ typedef struct ellcuda_ctx* ell_handle;
 
 typedef struct ell_create_desc {
     int32_t kind;              /* ELL_KIND_ELL: any n, matrix streamed from HBM, optionally row-sharded.
-                                  ELL_KIND_ELLSTABLE (src/ell_stable.rs): n <= 64, whole matrix, `mq` = the
+                                  ELL_KIND_ELLSTABLE (src/ell_stable.rs): n <= 2048, whole matrix, `mq` = the
                                   factor as the reference holds it (diagonal + strict upper triangle are
                                   read; need not be symmetric); its triangular recurrences neither stream
-                                  nor shard — large batches go through ellcuda_batch_solve               */
+                                  nor shard (one warp for n <= 64, one CTA above; serial in the reference's
+                                  summation order) — throughput comes from ellcuda_batch_solve           */
     int32_t device;
     int64_t n;
     double  kappa;             /* Ell::new_with_scalar(kappa,…) / new_with_matrix(kappa,…) */

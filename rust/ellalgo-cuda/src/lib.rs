@@ -14,7 +14,7 @@ use ellalgo_rs::arr::Arr;
 use ellalgo_rs::cutting_plane::{CutStatus, ParallelCut, SearchSpace, SingleCut, UpdateByCutChoice};
 use std::ffi::CStr;
 
-/// KIND = 0: `Ell` (src/ell.rs, any n, matrix in HBM); KIND = 1: `EllStable` (src/ell_stable.rs, n <= 64).
+/// KIND = 0: `Ell` (src/ell.rs, any n, matrix in HBM); KIND = 1: `EllStable` (src/ell_stable.rs, n <= 2048).
 pub struct EllCudaT<const KIND: i32> {
     h: sys::ell_handle,
     n: usize,

@@ -337,7 +337,8 @@ def test_ellstable_known_answers():  # src/ell_stable.rs:225-298
     assert np.array_equal(e.xc(), np.zeros(4)) and e.kappa == 0.01
 
 
-@pytest.mark.parametrize("n,start", [(2, "scalar"), (7, "diag"), (33, "upper"), (64, "upper"), (64, "scalar")])
+@pytest.mark.parametrize("n,start", [(2, "scalar"), (7, "diag"), (33, "upper"), (64, "upper"), (64, "scalar"),
+                                     (65, "upper"), (100, "diag"), (257, "upper"), (700, "scalar")])   # > 64: one-CTA kernel
 def test_ellstable_trajectory_bit_identical(ref, n, start):
     from ellalgo_rs_b200.ell import EllStable
     rng = np.random.default_rng(n)
@@ -379,7 +380,7 @@ def test_ellstable_driver_quasicvx():  # src/quasicvx.rs:95-105 test_feasible_st
     x, niter, _ = cutting_plane_optim(Quasicvx(), EllStable.new(np.array([10.0, 10.0]), np.zeros(2)), 0.0, Options(2000, 1e-8))
     assert x is not None and niter == 49
     with pytest.raises(Exception):
-        EllStable.new_with_scalar(1.0, np.zeros(65))
+        EllStable.new_with_scalar(1.0, np.zeros(2049))     # one-CTA kernel: n <= 2048
 
 
 # ---------------------------------------------------------------- §8f rank 4: the streaming GEMV on its own
