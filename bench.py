@@ -9,7 +9,12 @@ One JSON line on rank 0.  Headline workload (configs[2]): LowpassOracle n=32, 65
 Ell::new_with_scalar(40, 0), Options{50000, 1e-14}; a step = one ellcuda_batch_solve over the batch; the unit is one
 ellipsoid iteration = one update_core call (oracle evaluation included in the time).  `large_n` carries the second
 half of the metric (configs[4]): one n=16384 ellipsoid, ParallelCut(0.01, Some(0.10)) via update_bias_cut, 200
-updates after 20 warm-up, row-sharded over the N ranks with an NCCL allgather of grad_t per update.
+updates after 20 warm-up, row-sharded over the N ranks; the grad_t slabs are stored into every peer's memory over NVLink
+by the sweep kernel itself (`--exchange nccl` selects an NCCL all_gather per update instead).  At N=1 the large-n leg runs
+reduce_mode 0 (bit-identical, the headline) AND the tolerance modes the sharded runs use (2, 4, 8), so that scaling can be
+read like for like; at every N it carries a `parity` record: the first two updates from M = I on this very configuration
+against the CPU checker (tsq, kappa, all of xc, rank 0's slab of M).  `profit_1m` (configs[1]) and `lmi64` (configs[3]) are
+timed the same way as the headline, each with its own CPU figure from the same box.
 """
 from __future__ import annotations
 
@@ -90,6 +95,47 @@ def iterations_done(num_iters, exit_status):
     return int(num_iters.sum()) + int((exit_status != 5).sum())
 
 
+def cpu_leg(make, sample, ni_gpu, es_gpu, stride):
+    """the checker on a strided sample of the same batch: a CPU figure from this box and a parity check in one"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ellref_py as R
+    T = R.hardware_threads()
+    sp = make(sample)
+    t0 = time.perf_counter()
+    o = R.solve(sp, T)
+    dt = time.perf_counter() - t0
+    it = iterations_done(o.num_iters, o.exit_status)
+    idx = np.arange(sample) * stride
+    return {"value": it / dt, "unit": "iterations/s", "cores": T, "kind": "port",
+            "sample": f"{sample} problems (every {stride}-th of the batch), {it} iterations, {dt:.1f} s, std::thread over problems",
+            "sample_num_iters_and_status_identical": bool(np.array_equal(ni_gpu[idx], o.num_iters) and
+                                                          np.array_equal(es_gpu[idx], o.exit_status))}
+
+def strided(prob, stride, sample):
+    """problems 0, stride, 2*stride, ... of a host batch"""
+    sub = prob.slice(0, prob.count)
+    for name, width in (("kappa0", 1), ("xc0", prob.n), ("diag0", prob.n), ("mq0", prob.n * prob.n), ("gamma0", 1)):
+        a = getattr(prob, name)
+        if a is not None and prob._stride(a, width):
+            setattr(sub, name, np.ascontiguousarray(a.reshape(prob.count, -1)[::stride][:sample]))
+    if prob.params is not None and prob.params.ndim == 2 and prob.params.shape[0] == prob.count:
+        sub.params = np.ascontiguousarray(prob.params[::stride][:sample])
+    sub.count = sample
+    return sub
+
+
+def load_counters():
+    """per-kernel constants taken from the committed ncu captures (profiles/r02_counters.json, written by tools/ncu_counters.py)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_counters.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+COUNTERS = load_counters()
+
+
 # ================================================================================================== reference arm
 def run_reference(args, rank, world):
     if rank != 0:
@@ -141,6 +187,7 @@ def main():
     ap.add_argument("--skip-large-n", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-1m", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true")
     ap.add_argument("--per-gpu", type=int, default=PER_GPU)
     ap.add_argument("--large-n", type=int, default=LARGE_N)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
@@ -302,77 +349,148 @@ def main():
     large = None
     if not args.skip_large_n:
         n = args.large_n
-        mode = 0 if world == 1 else world    # k row segments keep 256 sweep warps per GPU when the slab has n/P columns
         grads = [torch.from_numpy(W.large_n_grad(n, k)).to(dev) for k in range(20)]
         cut = ParallelCut(*W.LARGE_N_CUT)
+        bytes_update = 16.0 * n * n                       # read M once + write M once (SURVEY §8d)
+        slab_bytes = bytes_update / world
         # kappa shrinks by ~1.5 % per update, so after ~290 of these cuts tsq falls under beta1^2 and the cut degrades to
         # a single/failed cut (cheaper sweeps).  Every phase therefore starts from a fresh M = I and stays below 260.
 
-        def fresh():
+        def fresh(mode, warm=LARGE_WARMUP):
             e = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local, exchange=args.exchange)
-            for k in range(LARGE_WARMUP):
+            for k in range(warm):
                 e.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
             return e
 
-        # phase A — throughput: 200 updates as 10 replays of a 20-update CUDA graph (launch latency hidden, north_star)
-        ell = fresh()
-        per_graph = 20
-        graph = None if args.no_graph else ell.capture(A.UPDATE_BIAS, grads[:per_graph], cut, stream)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ell.ell.launches
-        a0.record(stream)
-        if graph is not None:
-            for _ in range(LARGE_UPDATES // per_graph):
-                graph.replay()
-        else:
-            for k in range(LARGE_UPDATES):
+        def phases(mode):
+            """A: 200 updates as 10 replays of a 20-update CUDA graph; B: the sweep kernel alone (events around each launch)"""
+            ell = fresh(mode)
+            per_graph = 20
+            graph = None if args.no_graph else ell.capture(A.UPDATE_BIAS, grads[:per_graph], cut, stream)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ell.ell.launches
+            a0.record(stream)
+            if graph is not None:
+                for _ in range(LARGE_UPDATES // per_graph):
+                    graph.replay()
+            else:
+                for k in range(LARGE_UPDATES):
+                    ell.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
+            a1.record(stream)
+            barrier()
+            t_large = max_over_ranks(a0.elapsed_time(a1) / 1e3)
+            l_launch = (2 * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
+            status = int(ell.ell.last_status())
+            kind = ell.exchange_kind
+            del graph, ell
+            ell = fresh(mode)
+            ell.ell.set_timing(True)
+            sweeps = []
+            for k in range(60):
                 ell.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
-        a1.record(stream)
-        barrier()
-        t_large = max_over_ranks(a0.elapsed_time(a1) / 1e3)
-        l_launch = (4 * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
-        status = int(ell.ell.last_status())
-        exchange_kind = ell.exchange_kind
-        del graph, ell
+                sweeps.append(ell.ell.last_sweep_ms())
+            barrier()
+            status_b = int(ell.ell.last_status())
+            del ell
+            return {"reduce_mode": mode, "updates_per_s": LARGE_UPDATES / t_large, "ms_per_update": 1e3 * t_large / LARGE_UPDATES,
+                    "GBs": bytes_update * LARGE_UPDATES / t_large / 1e9, "sweep_ms": float(np.median(sweeps)),
+                    "sweep_GBs_per_gpu": slab_bytes / (float(np.median(sweeps)) * 1e-3) / 1e9,
+                    "last_status": status, "last_status_sweep_phase": status_b, "gpu_launches": int(l_launch), "exchange": kind}
 
-        # phase B — the sweep kernel alone: CUDA events around every sweep launch (same stream), eager, 60 updates
-        ell = fresh()
-        ell.ell.set_timing(True)
-        sweeps = []
-        for k in range(60):
-            ell.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
-            sweeps.append(ell.ell.last_sweep_ms())
-        barrier()
-        status_b = int(ell.ell.last_status())
-        sweep_ms = float(np.median(sweeps))
-        bytes_update = 16.0 * n * n                       # read M once + write M once (SURVEY §8d)
-        gbs = bytes_update * LARGE_UPDATES / t_large / 1e9
-        slab_bytes = bytes_update / world
+        def parity(mode):
+            """the first two updates from M = I on THIS configuration (n, reduce_mode, exchange, world) against the CPU checker
+            (oracle/, ~15 s per update on one host core, rank 0); every rank compares its own scalars and xc, rank 0 its slab"""
+            ell = fresh(mode, warm=0)
+            got = []
+            for k in range(2):
+                ell.update_async(A.UPDATE_BIAS, grads[k], cut)
+                got.append((int(ell.ell.last_status()), ell.tsq(), ell.kappa, ell.xc()))
+            slab = ell.ell.mq if rank == 0 else None
+            lo, hi = ell.lo, ell.hi
+            del ell
+            ref, secs = [None], []
+            if rank == 0:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import ellref_py as R
+                mq, xc = np.eye(n), np.zeros(n)
+                kap, tsq = C.c_double(1.0), C.c_double(0.0)
+                states = []
+                for k in range(2):
+                    g = W.large_n_grad(n, k)
+                    t0 = time.perf_counter()
+                    st = R.lib().ellref_ell_update_inplace(n, mq.ctypes.data, xc.ctypes.data, C.byref(kap), C.byref(tsq), 0, 1, 0,
+                                                           g.ctypes.data, W.LARGE_N_CUT[0], 1, W.LARGE_N_CUT[1], None)
+                    secs.append(time.perf_counter() - t0)
+                    states.append((int(st), tsq.value, kap.value, xc.copy()))
+                ref = [states]
+                den = float(np.abs(mq[lo:hi]).max())
+                m_err = float(np.abs(slab - mq[lo:hi]).max() / den)
+                m_same = bool(np.array_equal(slab, mq[lo:hi]))
+                del mq, slab
+            if world > 1:
+                dist.broadcast_object_list(ref, src=0)
+            worst, same, status_ok = 0.0, True, True
+            for (st, tsq_g, kap_g, xc_g), (st_r, tsq_r, kap_r, xc_r) in zip(got, ref[0]):
+                status_ok &= st == st_r
+                same &= tsq_g == tsq_r and kap_g == kap_r and bool(np.array_equal(xc_g, xc_r))
+                worst = max(worst, abs(tsq_g - tsq_r) / abs(tsq_r), abs(kap_g - kap_r) / abs(kap_r),
+                            float(np.abs(xc_g - xc_r).max() / np.abs(xc_r).max()))
+            worst = max_over_ranks(worst)
+            same = max_over_ranks(0.0 if same else 1.0) == 0.0
+            status_ok = max_over_ranks(0.0 if status_ok else 1.0) == 0.0
+            rec = {"against": "oracle/ (CPU restatement of src/ell.rs:97-137), updates 1 and 2 from M = I, ParallelCut(0.01, 0.10)",
+                   "n": n, "reduce_mode": mode, "world": world, "status_equal": status_ok,
+                   "max_rel_err_tsq_kappa_xc_over_ranks": worst, "bit_identical_tsq_kappa_xc": same, "tolerance": 1e-9}
+            if rank == 0:
+                rec.update({"rank0_slab_of_M_max_rel_err": m_err, "rank0_slab_of_M_bit_identical": m_same,
+                            "checker_s_per_update": secs})
+                ok = status_ok and worst <= 1e-9 and m_err <= 1e-9 and (mode != 0 or (same and m_same))
+                rec["pass"] = bool(ok)
+            return rec, secs
+
+        mode = 0 if world == 1 else world    # k row segments keep 256 sweep warps per GPU when the slab has n/P columns
+        main_phase = phases(mode)
+        by_mode = {str(mode): main_phase}
+        if world == 1:
+            for m in (2, 4, 8):              # the modes the sharded runs use, on one GPU: the like-for-like baselines
+                by_mode[str(m)] = phases(m)
+        par, ref_secs = parity(mode)
+        parities = {str(mode): par}
+        if world == 1 and not args.skip_cpu:
+            parities["8"], _ = parity(8)
+        sweep_ms = main_phase["sweep_ms"]
         large = {
             "metric": "Ell::update HBM GB/s at n=16384 (whole job, 16*n^2 algorithmic bytes per update)",
-            "value": gbs, "unit": "GB/s", "updates_per_s": LARGE_UPDATES / t_large, "ms_per_update": 1e3 * t_large / LARGE_UPDATES,
+            "value": main_phase["GBs"], "unit": "GB/s", "updates_per_s": main_phase["updates_per_s"],
+            "ms_per_update": main_phase["ms_per_update"],
             "n": n, "updates": LARGE_UPDATES, "warmup": LARGE_WARMUP, "scaling": "strong", "reduce_mode": mode,
-            "last_status": status, "last_status_sweep_phase": status_b, "gpu_launches": int(l_launch),
-            "cuda_graph": not args.no_graph,
-            "collective": None if world == 1 else f"{exchange_kind}: grad_t slabs (n*8 bytes in total) " + (
+            "last_status": main_phase["last_status"], "last_status_sweep_phase": main_phase["last_status_sweep_phase"],
+            "gpu_launches": main_phase["gpu_launches"], "cuda_graph": not args.no_graph,
+            "by_reduce_mode": by_mode,
+            "like_for_like": "N>1 runs reduce_mode=N (N ordered row segments per column block, 1e-9 gate); compare with "
+                             "by_reduce_mode[str(N)] of the N=1 line, not with its bit-identical reduce_mode 0 headline",
+            "parity": parities,
+            "collective": None if world == 1 else f"{main_phase['exchange']}: grad_t slabs (n*8 bytes in total) " + (
                 "stored into every peer's block over NVLink by the kernel that completes them; finish waits on device flags"
-                if exchange_kind == "p2p" else "NCCL all_gather_into_tensor per update"),
+                if main_phase["exchange"] == "p2p" else "NCCL all_gather_into_tensor per update"),
             "roofline": {"bound": "hbm", "kernel": "sweep_kernel (fused deferred rank-1 + GEMV, TMA-staged)",
                          "achieved": slab_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": slab_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": slab_bytes / (sweep_ms * 1e-3) / 1e9 / 8000.0,
                          "ms_per_launch": sweep_ms, "algorithmic_bytes_per_launch": slab_bytes,
-                         # ncu --set full of this very launch shape (n=16384, whole matrix): dram__bytes_read.sum 2.148194e9 +
-                         # dram__bytes_write.sum 2.089145e9 (profiles/r01b_prof_sweep2_raw.csv); not re-measured per run
-                         "traffic": 4237339000.0 if (world == 1 and n == 16384) else None,
-                         "traffic_source": "profiles/r01b_prof_sweep2_raw.csv" if (world == 1 and n == 16384) else None,
+                         "traffic": COUNTERS.get("sweep_n16384", {}).get("dram_bytes_per_launch") if (world == 1 and n == 16384) else None,
+                         "traffic_source": COUNTERS.get("sweep_n16384", {}).get("source") if (world == 1 and n == 16384) else None,
                          "timing": "median of 60 CUDA-event pairs around the sweep launches of an eager run (phase B)"},
         }
-        del ell
+        if rank == 0 and world == 1 and ref_secs:
+            dt = ref_secs[0]
+            large["cpu_baseline"] = {"value": 16.0 * n * n / dt / 1e9, "unit": "GB/s", "s_per_update": dt, "cores": 1, "kind": "port",
+                                     "sample": "1 update of the reference algorithm (single-threaded, as the Rust code is) — the first "
+                                               "update of the parity record"}
         # phase C — e2e: SearchSpace::update_bias_cut with a HOST gradient per call (H2D 8n bytes, D2H status), whole matrix
         if world == 1:
-            ell = fresh()
+            ell = fresh(0)
             hg = [torch.from_numpy(W.large_n_grad(n, k)).pin_memory() for k in range(20)]
             st = C.c_int32()
             K2 = 100
@@ -386,63 +504,114 @@ def main():
                             "timing": "host wall clock around synchronous ellcuda_update calls"}
             del ell
 
-    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    # ---------------------------------------------------------------- configs[1] and configs[3], timed like the headline
+    extras = {}
+    if not args.skip_extras:
+        def timed_batch(host, keys, reps=2):
+            dv = {k: torch.from_numpy(np.ascontiguousarray(getattr(host, k))).to(dev) for k in keys if getattr(host, k) is not None}
+            dp = BatchProblem(oracle_id=host.oracle_id, n=host.n, count=host.count, mode=host.mode, kind=host.kind,
+                              max_iters=host.max_iters, tolerance=host.tolerance, aux=list(host.aux), device=local, **dv)
+            res = {"xbest": torch.zeros(host.count, host.n, dtype=torch.float64, device=dev),
+                   "has_xbest": torch.zeros(host.count, dtype=torch.uint8, device=dev),
+                   "num_iters": torch.zeros(host.count, dtype=torch.int64, device=dev),
+                   "exit_status": torch.zeros(host.count, dtype=torch.int32, device=dev),
+                   "gamma": torch.zeros(host.count, dtype=torch.float64, device=dev)}
+            batch.solve_batch_device(dp, res, sptr)     # warm
+            barrier()
+            best = None
+            for _ in range(reps):
+                flush_buf.zero_()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record(stream)
+                batch.solve_batch_device(dp, res, sptr)
+                b1.record(stream)
+                barrier()
+                t = max_over_ranks(b0.elapsed_time(b1) / 1e3)
+                best = t if best is None else min(best, t)
+            ni, es = res["num_iters"].cpu().numpy(), res["exit_status"].cpu().numpy()
+            its = sum_over_ranks(float(iterations_done(ni, es)))
+            # e2e: host buffers through ellcuda_batch_solve (H2D + kernel + D2H inside the call)
+            host.device = local
+            t0 = time.perf_counter()
+            ho = batch.solve_batch(host, stream=sptr)
+            t_e2e = max_over_ranks(time.perf_counter() - t0)
+            its_e2e = sum_over_ranks(float(iterations_done(ho.num_iters, ho.exit_status)))
+            return {"value": its / best, "unit": "iterations/s", "ms": 1e3 * best, "problems_per_gpu": host.count,
+                    "problems_per_s": host.count * world / best, "iterations_per_gpu": iterations_done(ni, es),
+                    "e2e": {"value": its_e2e / t_e2e, "unit": "iterations/s", "timing": "host wall clock around ellcuda_batch_solve with host buffers"}}, ni, es
+
+        cpu_ok = rank == 0 and world == 1 and not args.skip_cpu
+        c1 = 1 << 20
+        hp = W.profit(c1, first=rank * c1)
+        rec, ni, es = timed_batch(hp, ("kappa0", "xc0", "diag0", "gamma0", "params"))
+        rec["workload"] = "configs[1]: ProfitOracle (Cobb-Douglas, n=2), 2^20 independent instances per GPU, Ell::new([100,100],[0,0]), default Options"
+        if cpu_ok:
+            rec["cpu_baseline"] = cpu_leg(lambda k: strided(hp, 16, k), 1 << 16, ni, es, 16)
+        extras["profit_1m"] = rec
+        for name, general, cnt_l in (("lmi64_diag", False, 1 << 15), ("lmi64_general", True, 1 << 15)):
+            hl = W.lmi(cnt_l, n=64, m=16, first=rank * cnt_l, general=general)
+            keys = ("kappa0", "xc0", "mq0", "gamma0", "table")
+            rec, ni, es = timed_batch(hl, keys)
+            rec["workload"] = ("configs[3]: LMIOracle (ldlt_mgr) feasibility, n=64, m=16, EllStable, 2^15 instances per GPU; " +
+                               ("C4b EllStable::new_with_matrix (general LDL^T recurrence)" if general else
+                                "C4a EllStable::new_with_scalar (the factor provably stays diagonal)"))
+            if cpu_ok:
+                rec["cpu_baseline"] = cpu_leg(lambda k, hl=hl: strided(hl, 16, k), 1 << 11, ni, es, 16)
+            extras[name] = rec
+
+    # ---------------------------------------------------------------- CPU baseline of the headline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import ellref_py as R
         T = R.hardware_threads()
-        sample = max(256 * T, 512)    # ≈10 s of CPU work on 16 threads
-        sp = W.lowpass(sample, table, n=N_TAPS)
-        t0 = time.perf_counter()
-        o = R.solve(sp, T)
-        dt = time.perf_counter() - t0
-        it = iterations_done(o.num_iters, o.exit_status)
-        cpu = {"value": it / dt, "unit": "iterations/s", "cores": T, "kind": "port",
-               "sample": f"first {sample} problems of the same lowpass n=32 batch ({it} iterations, {dt:.1f} s), std::thread over problems",
-               "per_core": it / dt / T}
-        # parity spot check on the sample (the checker as checker)
-        g_it = dres["num_iters"][:sample].cpu().numpy()
-        cpu["sample_num_iters_identical"] = bool(np.array_equal(g_it, o.num_iters))
-        if large is not None:
-            nn = args.large_n
-            mq, xc = np.eye(nn), np.zeros(nn)
-            kap, tsq = C.c_double(1.0), C.c_double(0.0)
-            g = W.large_n_grad(nn, 0)
-            reps = 1
-            t0 = time.perf_counter()
-            for k in range(reps):
-                R.lib().ellref_ell_update_inplace(nn, mq.ctypes.data, xc.ctypes.data, C.byref(kap), C.byref(tsq), 0, 1, 0,
-                                                  g.ctypes.data, W.LARGE_N_CUT[0], 1, W.LARGE_N_CUT[1], None)
-            dt = (time.perf_counter() - t0) / reps
-            large["cpu_baseline"] = {"value": 16.0 * nn * nn / dt / 1e9, "unit": "GB/s", "s_per_update": dt, "cores": 1,
-                                     "kind": "port", "sample": f"{reps} update of the reference algorithm (single-threaded, as the Rust code is)"}
+        sample = min(max(256 * T, 512), cnt)    # ≈10 s of CPU work on 16 threads
+        stride = max(cnt // sample, 1)          # spread over the whole batch, so the parity check is not just its head
+        cpu = cpu_leg(lambda k: strided(host, stride, k), sample, dres["num_iters"].cpu().numpy(),
+                      dres["exit_status"].cpu().numpy(), stride)
+        cpu["per_core"] = cpu["value"] / cpu["cores"]
 
     if rank == 0:
         alg_bytes = iters_step * 16.0 * N_TAPS * N_TAPS
+        ctr = COUNTERS.get("lowpass32", {})
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        # FP64 pipe: 16 lanes per SM sub-partition per clock = one warp instruction every 2 clocks; the reference's arithmetic
+        # is unfused (Rust never contracts a*b+c, the library is built -fmad=false), so an instruction is 32 flops, not 64
+        fp64_peak = sm_count * 4 * 16 * clk_mhz * 1e6 / 1e12
+        per_iter = ctr.get("fp64_warp_instr_per_iteration")
+        fp64_ach = None if per_iter is None else per_iter * 32.0 * iters_step / (kern_ms * 1e-3) / 1e12
         line = {
             "metric": "ellipsoid iterations/sec (batched n=32)", "value": value, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
             "iterations_per_step_per_gpu": iters_step,
-            "roofline": {"bound": "hbm", "kernel": "lowpass32_tmem_kernel (persistent, one warp per problem, M in tensor memory)",
-                         "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                         "ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         # real DRAM traffic is inputs + results only: ncu (4736-problem launch, profiles/r01c_prof_batch5_raw.csv)
-                         # read 0.75 MB, wrote < 1 MB — scaled by problem count here, not re-measured per run
-                         "traffic": float(h2d + d2h),
-                         "note": "equivalent-streaming figure of SURVEY.md 8d: 16*n^2 bytes per iteration (M read once, written "
-                                 "once) although M never leaves the SM (tensor memory + registers); the binding resource is the shared-memory "
-                                 "data pipe (80 %, profiles/r01c_prof_batch5_summary.txt); see large_n.roofline for the kernel that "
-                                 "really streams HBM"},
+            "roofline": {"bound": "fp64_pipe", "kernel": "lowpass32_tmem_kernel (persistent, one warp per problem, M in tensor memory)",
+                         "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": None if fp64_ach is None else fp64_ach / fp64_peak,
+                         "peak_source": f"{sm_count} SMs x 4 sub-partitions x 16 FP64 lanes/clk x {clk_mhz:.0f} MHz (sampled under load), "
+                                        "unfused DMUL/DADD = 1 flop per lane (the path may not contract to FMA); "
+                                        "tools/ubench_fp64_issue.cu measures the same 2 clk per warp instruction",
+                         "ms_per_launch": kern_ms,
+                         "fp64_warp_instr_per_iteration": per_iter, "flop_per_launch": None if per_iter is None else per_iter * 32.0 * iters_step,
+                         "counters_source": ctr.get("source"),
+                         "ncu_pipe_utilisation": ctr.get("pipes"),     # fp64 / shared-memory / issue-slot % of the same capture
+                         "traffic": ctr.get("dram_bytes_per_launch"), "traffic_source": ctr.get("source"),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at this launch "
+                                         "shape: inputs and results only, M never leaves the SM (tensor memory + registers)",
+                         "equivalent_streaming": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                  "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                                                  "algorithmic_bytes_per_launch": alg_bytes,
+                                                  "note": "SURVEY.md 8d / north_star's definition: 16*n^2 bytes per iteration as if M "
+                                                          "were streamed from HBM once per update; not a physical bandwidth"}},
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
             "bowl_1m": extra_1m,
+            "profit_1m": extras.get("profit_1m"), "lmi64_diag": extras.get("lmi64_diag"), "lmi64_general": extras.get("lmi64_general"),
             "large_n": large,
         }
         print(json.dumps(line), flush=True)

@@ -21,6 +21,8 @@ EXPORTS = [
     "ellcuda_exchange_block_ptr", "ellcuda_status_ptr", "ellcuda_last_status", "ellcuda_set_stream", "ellcuda_sync",
     "ellcuda_set_timing", "ellcuda_last_sweep_ms", "ellcuda_handle_launch_count",
     "ellcuda_math_probe", "ellcuda_last_error", "ellcuda_version", "ellcuda_device_count",
+    "ellcuda_batch_solve_multi", "ellcuda_create_sharded", "ellcuda_group_size",
+    "ellcuda_set_no_defer_trick", "ellcuda_set_use_parallel_cut",
 ]
 
 
@@ -72,6 +74,15 @@ def lib():
         H = C.c_void_p
         L.ellcuda_create.argtypes = [C.POINTER(_abi.CreateDesc), C.POINTER(H)]
         L.ellcuda_create.restype = C.c_int
+        L.ellcuda_create_sharded.argtypes = [C.POINTER(_abi.CreateDesc), C.c_int32, C.POINTER(C.c_int32), C.POINTER(H)]
+        L.ellcuda_create_sharded.restype = C.c_int
+        L.ellcuda_group_size.argtypes = [H]
+        L.ellcuda_group_size.restype = C.c_int32
+        for name in ("ellcuda_set_no_defer_trick", "ellcuda_set_use_parallel_cut"):
+            getattr(L, name).argtypes = [H, C.c_int32]
+            getattr(L, name).restype = C.c_int
+        L.ellcuda_batch_solve_multi.argtypes = [C.POINTER(_abi.BatchDesc), C.POINTER(_abi.BatchResult), C.c_int32, C.POINTER(C.c_int32)]
+        L.ellcuda_batch_solve_multi.restype = C.c_int
         L.ellcuda_clone.argtypes = [H, C.POINTER(H)]
         L.ellcuda_clone.restype = C.c_int
         L.ellcuda_destroy.argtypes = [H]

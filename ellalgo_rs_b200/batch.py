@@ -31,6 +31,21 @@ def solve_batch(prob: BatchProblem, out: BatchOutput | None = None, stream: int 
     return out
 
 
+def solve_batch_multi(prob: BatchProblem, devices, out: BatchOutput | None = None) -> BatchOutput:
+    """ellcuda_batch_solve_multi: the batch split into contiguous blocks over `devices` of this process (no launcher,
+    no collective); host buffers."""
+    if prob.on_device:
+        raise ValueError("solve_batch_multi takes host arrays")
+    if out is None:
+        out = BatchOutput.empty(prob.count, prob.n)
+    d = prob.to_desc(0)
+    r = out.to_result()
+    devs = (C.c_int32 * len(devices))(*devices)
+    check(lib().ellcuda_batch_solve_multi(C.byref(d), C.byref(r), len(devices), devs))
+    out.launches = lib().ellcuda_last_launch_count()
+    return out
+
+
 def solve_batch_device(prob: BatchProblem, res: dict, stream: int = 0) -> int:
     """Device-buffer call: every array of `prob` and every tensor in `res` (keys of ell_batch_result) is a CUDA
     tensor; the kernel is enqueued on `stream` and the call returns without synchronising.  Returns launches."""

@@ -310,15 +310,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
         const long long pid = (long long)pid_u;
         if (pid >= a.count) break;
 
-        {   // ---- Ell::new_with_matrix / new / new_with_scalar (src/ell.rs:31-78)
+        {   // ---- Ell::new / new_with_scalar (src/ell.rs:54-67); new_with_matrix starts go to batch_warp.cu's kernel
             double m[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                double v = 0.0;
-                if (a.mq0) v = a.mq0[pid * a.mq0_stride + (long long)lane * kN + j];
-                else if (j == lane) v = a.diag0 ? a.diag0[pid * a.diag0_stride + lane] : 1.0;
-                m[j] = v;
-            }
+            for (int j = 0; j < 32; ++j) m[j] = j == lane ? (a.diag0 ? a.diag0[pid * a.diag0_stride + lane] : 1.0) : 0.0;
             m_store(tm_m, m);
             tm_wait_st();
         }
@@ -428,8 +423,8 @@ int launch_variant(const BatchArgs& a, cudaStream_t s, int sm_count) {
 
 int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, long long* launches) {
     if (a.n != kN || a.aux[0] != 15 * kN) { set_error("lowpass32 kernel needs n = 32 and a 480-row spectrum"); return ELLCUDA_E_ARG; }
-    const char* e = getenv("ELLCUDA_LOWPASS_VARIANT");   // performance experiments only; results are identical
-    const int v = e ? atoi(e) : 0;
+    if (a.mq0) { set_error("lowpass32 kernel: diagonal starts only"); return ELLCUDA_E_ARG; }
+    const int v = ELL_ENV_INT("ELLCUDA_LOWPASS_VARIANT", 0);   // performance experiments only (read once); results are identical
     int rc;
     // Measured on B200 (tools/probe_tune.py, 16384 problems): spectrum entirely in shared memory 503 M iter/s (default);
     // last 8 columns of every row from TMEM 490 (the two-block select costs more issue slots than the shared-memory

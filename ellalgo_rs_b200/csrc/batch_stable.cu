@@ -544,7 +544,7 @@ int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int s
     // measured (n=64, m=16, diagonal start, 32768 problems): 8 warps 38.9, 16 58.9, 20 63.3, 24 65.4, 28 67.0 M iter/s —
     // the serial LDLT division chain wants every warp the register file can hold
     int cap = 28;
-    if (const char* e = getenv("ELLCUDA_LMI_WARPS")) cap = atoi(e);   // performance experiments
+    cap = ELL_ENV_INT("ELLCUDA_LMI_WARPS", 28);   // performance experiments (read once per process)
     if (cap < 1) cap = 1;
     if (cap > 28) cap = 28;
     if (!diag && cap > 16) cap = 16;   // the GENERAL variant is compiled for at most 512 threads

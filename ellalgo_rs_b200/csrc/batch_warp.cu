@@ -286,6 +286,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_warp_kernel(const Batc
         double best = 0.0;
         long long niter = 0;
         int exit_status = kExitMaxIt;
+        // Ell::new_with_matrix takes any matrix (src/ell.rs:31-41): M.g uses the rows as given (:102) until the first successful
+        // cut, whose rank-1 loop rewrites the upper triangle from the lower one (:117-128).  Until then M is still the input,
+        // so that mirror is a re-read of the input's lower triangle (a no-op in value for a symmetric input).  The driver
+        // returns at the first cut that is not a Success (src/cutting_plane.rs:308), so "first successful cut" = iteration 0.
 
         for (; niter < a.max_iters; ++niter) {  // cutting_plane_optim, src/cutting_plane.rs:299-311
             c.sx()[lane] = xc;
@@ -321,6 +325,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_warp_kernel(const Batc
             Rsd r;
             const int status = ell_calc(cc, which, cut, tsq, r);
             if (status != kSuccess) { exit_status = status; break; }
+            if (a.mq0 != nullptr && niter == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (lane_on && j > lane && j < n) m[j] = a.mq0[pid * a.mq0_stride + (long long)j * n + lane];
+            }
             const double rho_over_omega = r.rho / omega;
             xc -= rho_over_omega * gt;
             const double ratio = r.sigma / omega;
@@ -402,8 +411,7 @@ int launch_one(const BatchArgs& a, cudaStream_t s, int sm_count) {
 // ELLCUDA_TUNE=<k> selects an alternative warps-per-CTA / registers-per-thread variant (performance experiments only;
 // every variant computes identical results)
 int tuning_variant() {
-    const char* e = getenv("ELLCUDA_TUNE");
-    return e ? atoi(e) : 0;
+    return ELL_ENV_INT("ELLCUDA_TUNE", 0);   // read once per process
 }
 
 }  // namespace
@@ -435,7 +443,9 @@ int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_
         // The kernel is bound by shared-memory bandwidth (spectrum rows: 256 B per lane per row), so extra speculative
         // rows (R>1) cost more than the latency they hide; what pays is more resident warps without spilling.
         if (a.n != 32) rc = launch_one<OrLowpass<false, 1>, false, 8, 1>(a, s, sm_count);
-        else if (v == 0) return launch_batch_lowpass32(a, s, sm_count, launches);   // TMEM-assisted kernel, batch_lowpass.cu
+        // TMEM-assisted kernel, batch_lowpass.cu (diagonal starts; a new_with_matrix start, which may be non-symmetric and then
+        // needs the first-cut mirror below, runs in this file's kernel: 445 instead of 503 M iter/s)
+        else if (v == 0 && !a.mq0) return launch_batch_lowpass32(a, s, sm_count, launches);
         else if (v == 1) rc = launch_one<OrLowpass<true, 2, false, 16>, true, 8, 1>(a, s, sm_count);
         else if (v == 2) rc = launch_one<OrLowpass<true, 1, true>, true, 8, 1>(a, s, sm_count);
         else rc = launch_one<OrLowpass<true, 1, false, 8>, true, 16, 1>(a, s, sm_count);

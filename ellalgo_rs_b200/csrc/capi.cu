@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -104,26 +105,11 @@ int validate(const ell_batch_desc* d, const ell_batch_result* r) {
     return ELLCUDA_OK;
 }
 
-// the reference's matrix is symmetric by construction (src/ell.rs:117-128 mirrors every write); the kernels keep
-// one triangle authoritative, so an asymmetric new_with_matrix input is rejected rather than silently reinterpreted.
-bool host_mq_symmetric(const ell_batch_desc* d) {
-    const long long n = d->n;
-    const long long inst = d->mq0_stride ? d->count : 1;
-    for (long long p = 0; p < inst; ++p) {
-        const double* m = d->mq0 + p * d->mq0_stride;
-        for (long long i = 0; i < n; ++i)
-            for (long long j = 0; j < i; ++j) {
-                const double a = m[i * n + j], b = m[j * n + i];
-                if (!(a == b) && !(std::isnan(a) && std::isnan(b))) return false;
-            }
-    }
-    return true;
-}
-
 }  // namespace
 
 static int batch_solve_impl(const ell_batch_desc* d, const ell_batch_result* r) {
     g_last_launches = 0;
+    NvtxRange nvtx_range("ellcuda_batch_solve");
     int rc = validate(d, r);
     if (rc) return rc;
     DeviceInfo* di = nullptr;
@@ -132,10 +118,8 @@ static int batch_solve_impl(const ell_batch_desc* d, const ell_batch_result* r) 
     ELL_DEVICE_SCOPE(d->device);
     cudaStream_t s = d->stream ? (cudaStream_t)d->stream : di->stream;
     if (d->count == 0) return ELLCUDA_OK;
-    if (d->kind == ELL_KIND_ELL && d->mq0 && !d->on_device && !host_mq_symmetric(d)) {
-        set_error("mq0 must be symmetric");
-        return ELLCUDA_E_ARG;
-    }
+    // mq0 need not be symmetric (Ell::new_with_matrix takes any Arr, src/ell.rs:31-41): the kernels multiply by the rows as
+    // given until the first successful cut and then rewrite the upper triangle from the lower one, as src/ell.rs:117-128 does
 
     if ((d->oracle_id == ELL_ORACLE_LMI || d->oracle_id == ELL_ORACLE_LMI_OLD || d->oracle_id == ELL_ORACLE_LMI0) && !d->on_device &&
         d->table) {
@@ -245,6 +229,53 @@ extern "C" {
 
 int ellcuda_batch_solve(const ell_batch_desc* desc, const ell_batch_result* res) {
     return ellcuda::batch_solve_impl(desc, res);
+}
+
+// SURVEY.md §8b `ndev, devs` / §8e: independent problems, contiguous blocks, one host thread and one device per block.
+int ellcuda_batch_solve_multi(const ell_batch_desc* desc, const ell_batch_result* res, int32_t ndev, const int32_t* devs) {
+    using namespace ellcuda;
+    if (!desc || !res || !devs) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (ndev < 1 || ndev > 64) { set_error("ndev must be in [1, 64]"); return ELLCUDA_E_ARG; }
+    if (desc->on_device) { set_error("ellcuda_batch_solve_multi takes host buffers"); return ELLCUDA_E_ARG; }
+    if (desc->count < 0) { set_error("count must be non-negative"); return ELLCUDA_E_ARG; }
+    const int64_t cnt = desc->count, n = desc->n;
+    std::vector<int> rcs((size_t)ndev, ELLCUDA_OK);
+    std::vector<std::string> errs((size_t)ndev);
+    std::vector<long long> launches((size_t)ndev, 0);
+    auto work = [&](int r) {
+        const int64_t base = cnt / ndev, rem = cnt % ndev;
+        const int64_t lo = r * base + (r < rem ? r : rem), hi = lo + base + (r < rem ? 1 : 0);
+        ell_batch_desc d = *desc;
+        ell_batch_result o = *res;
+        d.count = hi - lo;
+        d.device = devs[r];
+        d.stream = nullptr;
+        auto adv = [&](const double*& p, int64_t stride) { if (p) p += lo * stride; };
+        adv(d.kappa0, d.kappa0_stride); adv(d.xc0, d.xc0_stride); adv(d.diag0, d.diag0_stride); adv(d.mq0, d.mq0_stride);
+        adv(d.gamma0, d.gamma0_stride); adv(d.params, d.params_stride);
+        if (o.xbest) o.xbest += lo * n;
+        if (o.has_xbest) o.has_xbest += lo;
+        if (o.num_iters) o.num_iters += lo;
+        if (o.exit_status) o.exit_status += lo;
+        if (o.gamma) o.gamma += lo;
+        if (o.tsq) o.tsq += lo;
+        if (o.xc) o.xc += lo * n;
+        if (o.kappa) o.kappa += lo;
+        rcs[r] = batch_solve_impl(&d, &o);
+        if (rcs[r]) errs[r] = g_err;          // thread-local on the worker: hand it to the caller
+        launches[r] = g_last_launches;
+    };
+    if (ndev == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int r = 0; r < ndev; ++r) th.emplace_back(work, r);
+        for (auto& t : th) t.join();
+    }
+    g_last_launches = 0;
+    for (int r = 0; r < ndev; ++r) g_last_launches += launches[r];
+    for (int r = 0; r < ndev; ++r)
+        if (rcs[r]) { set_error("device " + std::to_string(devs[r]) + ": " + errs[r]); return rcs[r]; }
+    return ELLCUDA_OK;
 }
 
 int64_t ellcuda_last_launch_count(void) { return ellcuda::g_last_launches; }

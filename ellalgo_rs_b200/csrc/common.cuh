@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/ellcuda.h"
 #include "ell_calc.cuh"
@@ -40,6 +43,25 @@ struct BatchArgs {
     double* kappa;
     unsigned long long* queue;  // dynamic work counter (persistent kernels)
 };
+
+// NVTX range for the scope of a host-side call (tracing); a no-op unless a profiler is attached
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
+// integer tuning switch from the environment, read once per process (performance experiments only)
+inline int env_int_once(const char* name, int dflt, int* cache, bool* have) {
+    if (!*have) {
+        const char* e = getenv(name);
+        *cache = e ? atoi(e) : dflt;
+        *have = true;
+    }
+    return *cache;
+}
+#define ELL_ENV_INT(name, dflt) ([]() -> int { static int v = 0; static bool have = false; return ::ellcuda::env_int_once(name, dflt, &v, &have); }())
 
 void set_error(const std::string& msg);
 void keep_mempool(int dev);

@@ -27,7 +27,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 
@@ -51,6 +54,8 @@ struct Scal {  // device-resident scalars of the Ell (src/ell.rs:9-16) + the def
     int status;     // CutStatus of the last finish
     unsigned long long epoch;   // peer exchange: number of the update in flight (device-resident so that a captured
                                 // CUDA graph of one update can be replayed); bumped at the end of finish
+    int failed;     // sticky: a peer wait timed out in some finish CTA; every later finish reports Unknown and the sweeps stop
+    int _pad;       // publishing, so that the peers time out too instead of consuming a half-updated state
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -313,6 +318,7 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     }
     const unsigned long long epoch = a.sc->epoch;
     const int attached = a.pt.nranks > 0;
+    if (attached && a.sc->failed) return;   // sticky peer failure: publish nothing, the peers' waits expire too
     const long long off = (attached ? (long long)(epoch & 1ULL) * a.n : 0) + a.c_glob0 + cl;
     if (!attached) {
         if (v0) a.own_blk[off] = acc0;
@@ -390,15 +396,18 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
     if (tid == 0) {
         s_epoch = sc->epoch;
         s_kappa_in = sc->kappa;
-        s_timeout = 0;
+        s_timeout = *reinterpret_cast<volatile int*>(&sc->failed);   // sticky: a handle that lost a peer stays failed
     }
     __syncthreads();
     const unsigned long long epoch = s_epoch;
     const int par = nranks > 0 ? (int)(epoch & 1ULL) : 0;
     const double* gt = blk + (long long)par * n;
-    if (nranks > 0) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
+    if (nranks > 0 && !s_timeout) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
         const unsigned long long* flags = xblk_flags(blk, n);
-        if (tid < nranks && !wait_flag(flags + tid, epoch)) s_timeout = 1;
+        if (tid < nranks && !wait_flag(flags + tid, epoch)) {
+            s_timeout = 1;
+            atomicExch(&sc->failed, 1);   // one decision for the whole handle: the CTA that publishes re-reads it
+        }
         __syncthreads();
     }
     if (!s_timeout) {
@@ -491,8 +500,15 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         if (prev == gridDim.x - 1) {   // last CTA: everyone has read sc
             *arrivals = 0;
             const double old_tsq = sc->tsq;
-            *sc = s_out;
-            if (s_timeout) sc->tsq = old_tsq;
+            const int failed = atomicOr(&sc->failed, 0);   // some CTA (maybe not this one) gave up waiting for a peer
+            Scal o = s_out;
+            if (failed) {   // the slices of xc/pend other CTAs may have written are void: the handle is dead from here on
+                o.status = kUnknown; o.pending = 0; o.ratio = 0.0; o.scale = 1.0; o.kappa = s_kappa_in; o.omega = 0.0;
+                o.tsq = old_tsq;
+            }
+            o.failed = failed;
+            o._pad = 0;
+            *sc = o;
         }
     }
 }
@@ -588,6 +604,19 @@ struct ellcuda_ctx {
     double* peer_blk[ellcuda::kMaxRanks] = {};   // every rank's exchange block as mapped in this process
     bool peer_opened[ellcuda::kMaxRanks] = {};   // mapped by cudaIpcOpenMemHandle (must be closed)
     CUtensorMap map;
+    // Ell::new_with_matrix with a NON-symmetric matrix (src/ell.rs:31-41 takes any Arr): until the first successful cut the
+    // reference multiplies by the rows as given (src/ell.rs:102) and leaves the matrix alone; the first successful cut then
+    // rewrites the upper triangle from the (updated) lower one (:117-128).  `S` holds the mirrored lower triangle from the
+    // start (what every rank-1 is applied to); `A` holds the matrix as given, transposed (A[i][c] = mq[c0+c][i], so that
+    // column sums over i are the reference's row sums), and is read by the sweeps while `asym_live`; the first Success
+    // (learned by a synchronous status read in finish) retires it.
+    bool asym_live = false;
+    double* A = nullptr;
+    CUtensorMap mapA;
+    // ellcuda_create_sharded: this handle is a GROUP — one slab handle per device of this process, peers attached by
+    // pointer; it owns no device memory itself and every entry point fans out over `parts`
+    std::vector<ellcuda_ctx*> parts;
+    double* ytmp = nullptr;     // group members: slab of a dot_mv result before it is copied to the caller's vector
     int which = 0;
     ellcuda::Cut cut{0.0, 0.0, false};
     bool timing = false;
@@ -601,7 +630,10 @@ namespace {
 
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
+    for (ellcuda_ctx* p : h->parts) free_ctx(p);
+    h->parts.clear();
     DevGuard guard(h->device);
+    cudaFree(h->A); cudaFree(h->ytmp);
     cudaFree(h->st_qu); cudaFree(h->st_scal); cudaFree(h->st_status);
     cudaFree(h->S); cudaFree(h->xc); cudaFree(h->gpad); cudaFree(h->gzero); cudaFree(h->gstage); cudaFreeHost(h->status_host);
     cudaFree(h->pend); cudaFree(h->partial); cudaFree(h->block_omega); cudaFree(h->counters); cudaFree(h->sc);
@@ -662,13 +694,20 @@ int alloc_ctx(ellcuda_ctx* h) {
 
 template <int CO, int R, int ST>
 int launch_sweep_t(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {
-    static bool attr_set = false;   // per instantiation
+    // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: one bit per device ordinal,
+    // per instantiation, set under a mutex (handles on several devices / host threads in one process)
+    static std::mutex mu;
+    static unsigned long long done_mask = 0;
     constexpr size_t smem = sweep_smem(CO, R, ST);
-    if (!attr_set) {
-        ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<CO, R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        const bool known = h->device < 64 && ((done_mask >> h->device) & 1ULL);
+        if (!known) {
+            ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<CO, R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (h->device < 64) done_mask |= 1ULL << h->device;
+        }
     }
-    sweep_kernel<CO, R, ST><<<grid, 32, smem, s>>>(h->map, a);
+    sweep_kernel<CO, R, ST><<<grid, 32, smem, s>>>(h->asym_live ? h->mapA : h->map, a);
     return ELLCUDA_OK;
 }
 
@@ -692,7 +731,7 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev, double* plain_out = nullp
     const bool flush = g_dev == nullptr;
     if (flush) {
         h->gsrc = h->gzero;
-    } else if (h->n % kRowsMax == 0 && (reinterpret_cast<uintptr_t>(g_dev) & 15) == 0) {
+    } else if (h->n % kRowsMax == 0 && h->n % h->tile_rows == 0 && (reinterpret_cast<uintptr_t>(g_dev) & 15) == 0) {
         h->gsrc = g_dev;      // tiles never read past n: the caller's buffer is loaded directly (no copy kernel)
     } else {
         const int thr = 256;
@@ -806,11 +845,15 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     ELL_CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
     if (prop.major < 10) { set_error("libellcuda is built for sm_100a (B200) only"); return ELLCUDA_E_CUDA; }
     ELL_DEVICE_SCOPE(d->device);
-    if (d->mq) {  // symmetric input required (see capi.cu)
+    bool asym = false;
+    if (d->mq) {  // Ell::new_with_matrix takes any Arr (src/ell.rs:31-41); a non-symmetric one needs the `A` copy (see ellcuda_ctx)
         const long long n = d->n;
-        for (long long i = 0; i < n; ++i)
+        for (long long i = 0; i < n && !asym; ++i)
             for (long long j = 0; j < i; ++j)
-                if (!(d->mq[i * n + j] == d->mq[j * n + i])) { set_error("mq must be symmetric"); return ELLCUDA_E_ARG; }
+                if (!(d->mq[i * n + j] == d->mq[j * n + i]) && !(d->mq[i * n + j] != d->mq[i * n + j] && d->mq[j * n + i] != d->mq[j * n + i])) {
+                    asym = true;
+                    break;
+                }
     }
     ellcuda_ctx* h = new ellcuda_ctx();
     h->device = d->device;
@@ -829,7 +872,29 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     cudaStream_t s = h->stream;
     cudaError_t e = cudaSuccess;
     const long long n = h->n;
-    if (d->mq) {  // column block [c0, c0+w) of the row-major host matrix
+    std::vector<double> stage_l, stage_a;   // must outlive the asynchronous copies below
+    if (d->mq && asym) {
+        // S <- column block of the mirrored lower triangle; A <- the slab's rows as given, transposed
+        const long long w = h->w, c0 = h->c0;
+        stage_l.resize((size_t)n * w);
+        stage_a.resize((size_t)n * w);
+        for (long long i = 0; i < n; ++i)
+            for (long long c = 0; c < w; ++c) {
+                const long long j = c0 + c;
+                stage_l[(size_t)i * w + c] = i >= j ? d->mq[i * n + j] : d->mq[j * n + i];
+                stage_a[(size_t)i * w + c] = d->mq[j * n + i];
+            }
+        e = cudaMalloc(&h->A, (size_t)n * h->ld * 8);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->A, 0, (size_t)n * h->ld * 8, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->S, 0, (size_t)n * h->ld * 8, s);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(h->S, (size_t)h->ld * 8, stage_l.data(), (size_t)w * 8, (size_t)w * 8, (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(h->A, (size_t)h->ld * 8, stage_a.data(), (size_t)w * 8, (size_t)w * 8, (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            rc = make_tensor_map(&h->mapA, h->A, n, h->w, h->ld, h->tile_rows, h->cols);
+            if (rc) { cudaStreamSynchronize(s); free_ctx(h); return rc; }
+            h->asym_live = true;
+        }
+    } else if (d->mq) {  // column block [c0, c0+w) of the row-major host matrix
         e = cudaMemcpy2DAsync(h->S, (size_t)h->ld * 8, d->mq + h->c0, (size_t)n * 8, (size_t)h->w * 8, (size_t)n, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && h->ld != h->w) e = cudaMemset2DAsync(h->S + h->w, (size_t)h->ld * 8, 0, 8, (size_t)n, s);
     } else {
@@ -856,8 +921,25 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     return ELLCUDA_OK;
 }
 
+static int attach_group(ellcuda_ctx* g);
+
 int ellcuda_clone(ell_handle h, ell_handle* out) {
     if (!h || !out) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {   // group: clone every slab, then attach the clones to each other
+        ellcuda_ctx* g = new ellcuda_ctx();
+        g->kind = h->kind; g->device = h->device; g->n = h->n; g->w = h->w;
+        g->reduce_mode = h->reduce_mode; g->no_defer = h->no_defer; g->use_parallel = h->use_parallel;
+        for (ellcuda_ctx* p : h->parts) {
+            ell_handle c = nullptr;
+            const int rc = ellcuda_clone(p, &c);
+            if (rc) { free_ctx(g); return rc; }
+            g->parts.push_back(c);
+        }
+        const int rc = attach_group(g);
+        if (rc) { free_ctx(g); return rc; }
+        *out = g;
+        return ELLCUDA_OK;
+    }
     ELL_DEVICE_SCOPE(h->device);
     if (h->kind == ELL_KIND_ELLSTABLE) {
         const long long n = h->n, tri = n * (n + 1) / 2;
@@ -897,6 +979,15 @@ int ellcuda_clone(ell_handle h, ell_handle* out) {
     e = cudaMemcpyAsync(c->S, h->S, (size_t)n * h->ld * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->xc, h->xc, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->pend, h->pend, (size_t)(h->npad + kColsMax + 2) * 16, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && h->asym_live) {
+        e = cudaMalloc(&c->A, (size_t)n * h->ld * 8);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->A, h->A, (size_t)n * h->ld * 8, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) {
+            rc = make_tensor_map(&c->mapA, c->A, n, c->w, c->ld, c->tile_rows, c->cols);
+            if (rc) { cudaStreamSynchronize(s); free_ctx(c); return rc; }
+            c->asym_live = true;
+        }
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&sc_h, h->sc, sizeof(Scal), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     sc_h.epoch = 1;
@@ -911,6 +1002,7 @@ void ellcuda_destroy(ell_handle h) { free_ctx(h); }
 
 int ellcuda_xc(ell_handle h, double* out) {
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) return ellcuda_xc(h->parts[0], out);   // xc is replicated, identical on every slab handle
     ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaMemcpyAsync(out, h->xc, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -919,6 +1011,10 @@ int ellcuda_xc(ell_handle h, double* out) {
 
 int ellcuda_set_xc(ell_handle h, const double* x) {
     if (!h || !x) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {
+        for (ellcuda_ctx* p : h->parts) { const int rc = ellcuda_set_xc(p, x); if (rc) return rc; }
+        return ELLCUDA_OK;
+    }
     ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaMemcpyAsync(h->xc, x, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -943,6 +1039,7 @@ static int read_stable_scal(ell_handle h, int which, double* out) {
 
 int ellcuda_tsq(ell_handle h, double* out) {
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) return ellcuda_tsq(h->parts[0], out);
     if (h->kind == ELL_KIND_ELLSTABLE) return read_stable_scal(h, 1, out);
     Scal sc;
     int rc = read_scal(h, &sc);
@@ -953,6 +1050,7 @@ int ellcuda_tsq(ell_handle h, double* out) {
 
 int ellcuda_kappa(ell_handle h, double* out) {
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) return ellcuda_kappa(h->parts[0], out);
     if (h->kind == ELL_KIND_ELLSTABLE) return read_stable_scal(h, 0, out);
     Scal sc;
     int rc = read_scal(h, &sc);
@@ -963,6 +1061,10 @@ int ellcuda_kappa(ell_handle h, double* out) {
 
 int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row-major
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {   // group: the slabs in row order make up the whole matrix
+        for (ellcuda_ctx* p : h->parts) { const int rc = ellcuda_get_mq(p, out + p->c0 * p->n); if (rc) return rc; }
+        return ELLCUDA_OK;
+    }
     ELL_DEVICE_SCOPE(h->device);
     if (h->kind == ELL_KIND_ELLSTABLE) {   // the factor: diagonal + strict upper; the strict lower (scratch in the reference) is 0
         const long long n = h->n, tri = n * (n + 1) / 2;
@@ -980,7 +1082,7 @@ int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row
     double* tmp = nullptr;
     ELL_CUDA_TRY(cudaMallocAsync((void**)&tmp, (size_t)h->w * h->n * 8, h->stream));
     dim3 grid((unsigned)((h->w + 31) / 32), (unsigned)((h->n + 31) / 32)), block(32, 8);
-    transpose_kernel<<<grid, block, 0, h->stream>>>(h->S, h->ld, tmp, h->n, h->w);
+    transpose_kernel<<<grid, block, 0, h->stream>>>(h->asym_live ? h->A : h->S, h->ld, tmp, h->n, h->w);
     h->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, (size_t)h->w * h->n * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -993,6 +1095,18 @@ int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row
 int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev) {
     if (!h || !x_dev || !y_dev) { set_error("null argument"); return ELLCUDA_E_ARG; }
     if (h->kind != ELL_KIND_ELL) { set_error("dot_mv needs an Ell handle"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {   // group: every device forms its rows of y from its own copy of x; y_dev receives all n entries
+        for (ellcuda_ctx* p : h->parts) {
+            ELL_DEVICE_SCOPE(p->device);
+            if (!p->ytmp) ELL_CUDA_TRY(cudaMalloc(&p->ytmp, (size_t)p->ld_part * 8));
+            ELL_CUDA_TRY(cudaMemcpyAsync(p->gstage, x_dev, (size_t)p->n * 8, cudaMemcpyDefault, p->stream));
+            int rc = ellcuda_dot_mv(p, p->gstage, p->ytmp);
+            if (rc) return rc;
+            ELL_CUDA_TRY(cudaMemcpyAsync(y_dev + p->c0, p->ytmp, (size_t)p->w * 8, cudaMemcpyDefault, p->stream));
+        }
+        for (ellcuda_ctx* p : h->parts) { const int rc = ellcuda_sync(p); if (rc) return rc; }
+        return ELLCUDA_OK;
+    }
     ELL_DEVICE_SCOPE(h->device);
     Scal sc;
     int rc = read_scal(h, &sc);
@@ -1007,6 +1121,15 @@ int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev) {
 int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, double beta0, int32_t has_beta1, double beta1) {
     if (!h || !grad_dev) { set_error("null argument"); return ELLCUDA_E_ARG; }
     if (which < ELL_UPDATE_BIAS || which > ELL_UPDATE_Q) { set_error("bad update selector"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {   // group: the gradient is copied to every device (it must be complete when this is called), then
+        for (ellcuda_ctx* p : h->parts) {   // every slab's sweep is enqueued before any finish can start waiting for peers
+            ELL_DEVICE_SCOPE(p->device);
+            ELL_CUDA_TRY(cudaMemcpyAsync(p->gstage, grad_dev, (size_t)p->n * 8, cudaMemcpyDefault, p->stream));
+            const int rc = ellcuda_update_begin(p, which, p->gstage, beta0, has_beta1, beta1);
+            if (rc) return rc;
+        }
+        return ELLCUDA_OK;
+    }
     ELL_DEVICE_SCOPE(h->device);
     h->which = which;
     h->cut = has_beta1 > 0 ? parallel_cut(beta0, beta1) : single_cut(beta0);
@@ -1020,6 +1143,10 @@ int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, do
 
 int ellcuda_update_finish(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {
+        for (ellcuda_ctx* p : h->parts) { const int rc = ellcuda_update_finish(p); if (rc) return rc; }
+        return ELLCUDA_OK;
+    }
     if (h->kind == ELL_KIND_ELLSTABLE) return ELLCUDA_OK;
     ELL_DEVICE_SCOPE(h->device);
     if (!h->gsrc) { set_error("ellcuda_update_finish without ellcuda_update_begin"); return ELLCUDA_E_ARG; }
@@ -1030,12 +1157,58 @@ int ellcuda_update_finish(ell_handle h) {
                                                                      h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode, h->nranks);
     ELL_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
+    if (h->asym_live) {   // non-symmetric start: the host must learn of the first Success (see ellcuda_ctx::asym_live)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(h->stream, &cap);
+        if (cap != cudaStreamCaptureStatusNone) {
+            set_error("a handle created from a non-symmetric matrix cannot be captured in a CUDA graph before its first successful cut");
+            return ELLCUDA_E_ARG;
+        }
+        int32_t st = ELL_UNKNOWN;
+        const int rc = ellcuda_last_status(h, &st);
+        if (rc) return rc;
+        if (st == ELL_SUCCESS) {
+            h->asym_live = false;
+            cudaFree(h->A);
+            h->A = nullptr;
+        }
+    }
+    return ELLCUDA_OK;
+}
+
+int ellcuda_set_no_defer_trick(ell_handle h, int32_t on) {   // `pub no_defer_trick` written after new(), src/ell.rs:10, 342-344
+    if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    if (h->kind != ELL_KIND_ELL) { set_error("EllStable has no no_defer_trick (src/ell_stable.rs:9-15)"); return ELLCUDA_E_ARG; }
+    h->no_defer = on != 0;   // read by the next finish (src/ell.rs:132-135); updates already made are not revisited, as in the reference
+    for (ellcuda_ctx* p : h->parts) p->no_defer = h->no_defer;
+    return ELLCUDA_OK;
+}
+
+int ellcuda_set_use_parallel_cut(ell_handle h, int32_t on) {   // EllCalc::use_parallel_cut, src/ell_calc.rs:630; Ell/EllStable helper
+    if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    h->use_parallel = on != 0;
+    for (ellcuda_ctx* p : h->parts) p->use_parallel = h->use_parallel;
     return ELLCUDA_OK;
 }
 
 int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double beta0, int32_t has_beta1, double beta1,
                    int32_t* out_status) {
     if (!h || !grad_host || !out_status) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {   // group: host gradient to every device, all sweeps, all finishes, then the (identical) status
+        nvtxRangePushA("ellcuda_update[group]");
+        int rc = ELLCUDA_OK;
+        for (ellcuda_ctx* p : h->parts) {
+            DevGuard guard(p->device);
+            cudaError_t e = guard.err;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(p->gstage, grad_host, (size_t)p->n * 8, cudaMemcpyHostToDevice, p->stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "group gradient upload", __FILE__, __LINE__); break; }
+            if ((rc = ellcuda_update_begin(p, which, p->gstage, beta0, has_beta1, beta1))) break;
+        }
+        if (!rc) rc = ellcuda_update_finish(h);
+        if (!rc) rc = ellcuda_last_status(h, out_status);
+        nvtxRangePop();
+        return rc;
+    }
     if (h->w != h->n) { set_error("ellcuda_update needs a whole-matrix handle; sharded handles use update_begin/finish"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaMemcpyAsync(h->gstage, grad_host, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1045,11 +1218,26 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double 
     return ellcuda_last_status(h, out_status);
 }
 
-double* ellcuda_grad_t_ptr(ell_handle h) { return h && h->kind == ELL_KIND_ELL ? h->xblk : nullptr; }
-int32_t* ellcuda_status_ptr(ell_handle h) { return !h ? nullptr : h->kind == ELL_KIND_ELLSTABLE ? h->st_status : &h->sc->status; }
+double* ellcuda_grad_t_ptr(ell_handle h) { return h && h->kind == ELL_KIND_ELL ? h->xblk : nullptr; }   // null for a group
+int32_t* ellcuda_status_ptr(ell_handle h) {
+    if (h && !h->parts.empty()) h = h->parts[0];
+    return !h ? nullptr : h->kind == ELL_KIND_ELLSTABLE ? h->st_status : &h->sc->status;
+}
 
 int ellcuda_last_status(ell_handle h, int32_t* out_status) {
     if (!h || !out_status) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {   // every device is drained; the slab handles hold identical scalars, any mismatch is a lost peer
+        int32_t st0 = ELL_UNKNOWN;
+        for (size_t r = 0; r < h->parts.size(); ++r) {
+            int32_t st = ELL_UNKNOWN;
+            const int rc = ellcuda_last_status(h->parts[r], &st);
+            if (rc) return rc;
+            if (r == 0) st0 = st;
+            else if (st != st0) st0 = ELL_UNKNOWN;
+        }
+        *out_status = st0;
+        return ELLCUDA_OK;
+    }
     ELL_DEVICE_SCOPE(h->device);
     const int* src = h->kind == ELL_KIND_ELLSTABLE ? h->st_status : &h->sc->status;
     ELL_CUDA_TRY(cudaMemcpyAsync(h->status_host, src, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1060,6 +1248,7 @@ int ellcuda_last_status(ell_handle h, int32_t* out_status) {
 
 int ellcuda_exchange_export(ell_handle h, void* handle_out) {
     if (!h || !handle_out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) { set_error("a group handle manages its own exchange"); return ELLCUDA_E_ARG; }
     if (h->kind != ELL_KIND_ELL) { set_error("EllStable does not shard"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
     cudaIpcMemHandle_t ipc;
@@ -1072,6 +1261,7 @@ int ellcuda_exchange_export(ell_handle h, void* handle_out) {
 void* ellcuda_exchange_block_ptr(ell_handle h) { return h ? h->xblk : nullptr; }
 
 static int attach_common(ell_handle h, int32_t nranks, int32_t rank) {
+    if (!h->parts.empty()) { set_error("a group handle manages its own exchange"); return ELLCUDA_E_ARG; }
     if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) { set_error("bad nranks/rank"); return ELLCUDA_E_ARG; }
     if (h->nranks > 0) { set_error("exchange already attached"); return ELLCUDA_E_ARG; }
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1087,8 +1277,66 @@ int ellcuda_exchange_attach_ptrs(ell_handle h, int32_t nranks, int32_t rank, voi
     for (int r = 0; r < nranks; ++r) {
         h->peer_blk[r] = r == rank ? h->xblk : (double*)blocks[r];
         if (!h->peer_blk[r]) { set_error("null peer block"); return ELLCUDA_E_ARG; }
+        if (r == rank) continue;
+        // a block on another device of this process: the sweep stores into it over NVLink, which needs peer access enabled
+        cudaPointerAttributes pa;
+        ELL_CUDA_TRY(cudaPointerGetAttributes(&pa, h->peer_blk[r]));
+        if (pa.type == cudaMemoryTypeDevice && pa.device != h->device) {
+            int can = 0;
+            ELL_CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, pa.device));
+            if (!can) { set_error("no peer access between the devices of this exchange"); return ELLCUDA_E_COMM; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(pa.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__); return ELLCUDA_E_COMM; }
+        }
     }
     h->nranks = nranks; h->rank = rank;
+    return ELLCUDA_OK;
+}
+
+// attaches the slab handles of a group to each other (all in this process)
+static int attach_group(ellcuda_ctx* g) {
+    const int P = (int)g->parts.size();
+    if (P < 2) return ELLCUDA_OK;
+    void* blocks[kMaxRanks];
+    for (int r = 0; r < P; ++r) blocks[r] = g->parts[r]->xblk;
+    for (int r = 0; r < P; ++r) {
+        const int rc = ellcuda_exchange_attach_ptrs(g->parts[r], P, r, blocks);
+        if (rc) return rc;
+    }
+    return ELLCUDA_OK;
+}
+
+// Row-sharded Ell over `ndev` devices of THIS process (`ndev, devs`): one slab handle per device, rows split
+// as evenly as possible, the exchange blocks attached by pointer with peer access.  The returned handle is used like any
+// other Ell handle (ellcuda_update with a host gradient, xc, tsq, kappa, get_mq, dot_mv, clone, destroy); no launcher, no
+// torch, no NCCL — a Rust host needs nothing but this library.
+int ellcuda_create_sharded(const ell_create_desc* d, int32_t ndev, const int32_t* devs, ell_handle* out) {
+    if (!d || !out || !devs) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    *out = nullptr;
+    if (d->kind != ELL_KIND_ELL) { set_error("EllStable does not shard (its recurrences are triangular)"); return ELLCUDA_E_ARG; }
+    if (ndev < 1 || ndev > kMaxRanks) { set_error("ndev must be in [1, 16]"); return ELLCUDA_E_ARG; }
+    if (d->n < ndev) { set_error("fewer rows than devices"); return ELLCUDA_E_ARG; }
+    if (d->row_begin != 0 || (d->row_end != 0 && d->row_end != d->n)) { set_error("ellcuda_create_sharded splits the rows itself"); return ELLCUDA_E_ARG; }
+    // devs may repeat: several slabs then share a device, each on its own stream (how the tests run a group on one GPU)
+    ellcuda_ctx* g = new ellcuda_ctx();
+    g->kind = ELL_KIND_ELL; g->device = devs[0]; g->n = d->n; g->w = d->n;
+    g->reduce_mode = d->reduce_mode; g->no_defer = d->no_defer_trick; g->use_parallel = d->use_parallel_cut;
+    const long long base = d->n / ndev, rem = d->n % ndev;
+    for (int r = 0; r < ndev; ++r) {
+        ell_create_desc dr = *d;
+        dr.device = devs[r];
+        dr.row_begin = r * base + (r < rem ? r : rem);
+        dr.row_end = dr.row_begin + base + (r < rem ? 1 : 0);
+        dr.stream = nullptr;   // every slab runs on its own stream of its own device
+        ell_handle c = nullptr;
+        const int rc = ellcuda_create(&dr, &c);
+        if (rc) { free_ctx(g); return rc; }
+        g->parts.push_back(c);
+    }
+    const int rc = attach_group(g);
+    if (rc) { free_ctx(g); return rc; }
+    *out = g;
     return ELLCUDA_OK;
 }
 
@@ -1120,6 +1368,7 @@ int ellcuda_exchange_attach(ell_handle h, int32_t nranks, int32_t rank, const vo
 
 int ellcuda_set_stream(ell_handle h, void* stream) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) { set_error("a group handle runs on its own per-device streams"); return ELLCUDA_E_ARG; }
     ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
@@ -1133,6 +1382,10 @@ int ellcuda_set_stream(ell_handle h, void* stream) {
 
 int ellcuda_sync(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) {
+        for (ellcuda_ctx* p : h->parts) { const int rc = ellcuda_sync(p); if (rc) return rc; }
+        return ELLCUDA_OK;
+    }
     ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ELLCUDA_OK;
@@ -1142,10 +1395,16 @@ int ellcuda_set_timing(ell_handle h, int32_t on) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
     h->timing = on != 0;
     h->timed = false;
+    for (ellcuda_ctx* p : h->parts) { p->timing = h->timing; p->timed = false; }
     return ELLCUDA_OK;
 }
 
 float ellcuda_last_sweep_ms(ell_handle h) {
+    if (h && !h->parts.empty()) {   // group: the slowest slab
+        float worst = -1.0f;
+        for (ellcuda_ctx* p : h->parts) { const float ms = ellcuda_last_sweep_ms(p); if (ms > worst) worst = ms; }
+        return worst;
+    }
     if (!h || !h->timed) return -1.0f;
     float ms = -1.0f;
     if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
@@ -1153,6 +1412,12 @@ float ellcuda_last_sweep_ms(ell_handle h) {
     return ms;
 }
 
-int64_t ellcuda_handle_launch_count(ell_handle h) { return h ? h->launches : 0; }
+int64_t ellcuda_handle_launch_count(ell_handle h) {
+    if (!h) return 0;
+    long long total = h->launches;
+    for (ellcuda_ctx* p : h->parts) total += p->launches;
+    return total;
+}
+int32_t ellcuda_group_size(ell_handle h) { return !h ? 0 : h->parts.empty() ? 1 : (int32_t)h->parts.size(); }
 
 }  // extern "C"

@@ -34,7 +34,9 @@ class Ell:
     KIND = _abi.KIND_ELL
 
     def __init__(self, kappa, xc, mq=None, diag=None, *, device=0, no_defer_trick=False, use_parallel_cut=True,
-                 rows=None, reduce_mode=0, stream=0, _handle=None):
+                 rows=None, reduce_mode=0, stream=0, devices=None, _handle=None):
+        """devices=[d0, d1, …]: rows sharded over these devices of this process (ellcuda_create_sharded); the object is
+        then used exactly like a single-device one."""
         self._keep = []
         if _handle is not None:
             self._h = _handle
@@ -59,11 +61,42 @@ class Ell:
         d.reduce_mode = reduce_mode
         d.stream = stream
         h = C.c_void_p()
-        check(lib().ellcuda_create(C.byref(d), C.byref(h)))
+        if devices is not None:
+            devs = (C.c_int32 * len(devices))(*devices)
+            d.row_begin, d.row_end = 0, n
+            check(lib().ellcuda_create_sharded(C.byref(d), len(devices), devs, C.byref(h)))
+            device = devices[0]
+        else:
+            check(lib().ellcuda_create(C.byref(d), C.byref(h)))
         self._h = h
         self.n = n
         self.rows = (d.row_begin, d.row_end)
-        self.no_defer_trick = bool(no_defer_trick)
+        self.device = device
+        self._no_defer_trick = bool(no_defer_trick)
+        self._use_parallel_cut = bool(use_parallel_cut)
+
+    # ---- the reference's public knobs, writable after construction (src/ell.rs:10, 342-344; src/ell_calc.rs:630)
+    @property
+    def no_defer_trick(self) -> bool:
+        return self._no_defer_trick
+
+    @no_defer_trick.setter
+    def no_defer_trick(self, on: bool):
+        check(lib().ellcuda_set_no_defer_trick(self._h, int(bool(on))))
+        self._no_defer_trick = bool(on)
+
+    @property
+    def use_parallel_cut(self) -> bool:
+        return self._use_parallel_cut
+
+    @use_parallel_cut.setter
+    def use_parallel_cut(self, on: bool):
+        check(lib().ellcuda_set_use_parallel_cut(self._h, int(bool(on))))
+        self._use_parallel_cut = bool(on)
+
+    @property
+    def group_size(self) -> int:
+        return int(lib().ellcuda_group_size(self._h))
 
     # ---- constructors, src/ell.rs:31-78
     @classmethod
@@ -95,7 +128,8 @@ class Ell:
         h = C.c_void_p()
         check(lib().ellcuda_clone(self._h, C.byref(h)))
         e = type(self)(0, None, _handle=h)
-        e.n, e.rows, e.no_defer_trick = self.n, self.rows, self.no_defer_trick
+        e.n, e.rows, e.device = self.n, self.rows, self.device
+        e._no_defer_trick, e._use_parallel_cut = self._no_defer_trick, self._use_parallel_cut
         return e
 
     # ---- SearchSpace, src/ell.rs:140-180
@@ -157,9 +191,10 @@ class Ell:
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.shape != (self.n,):
             raise ValueError("x must have n entries")  # assert_eq!(self.cols, x.len())
-        xd = torch.from_numpy(x).cuda()
-        yd = torch.empty(self.rows[1] - self.rows[0], dtype=torch.float64, device=xd.device)
-        torch.cuda.synchronize()
+        dev = f"cuda:{self.device}"          # the handle's device, not torch's current one
+        xd = torch.from_numpy(x).to(dev)
+        yd = torch.empty(self.rows[1] - self.rows[0], dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(self.device)
         self.dot_mv_device(xd.data_ptr(), yd.data_ptr())
         self.sync()
         return yd.cpu().numpy()

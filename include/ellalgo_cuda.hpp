@@ -64,6 +64,7 @@ struct EllConfig {
     bool no_defer_trick = false;    // src/ell.rs:10
     bool use_parallel_cut = true;   // src/ell_calc.rs:630
     int reduce_mode = 0;            // 0 = bit-identical to the reference's summation order
+    std::vector<int> devices;       // non-empty: rows sharded over these devices of this process (ellcuda_create_sharded)
 };
 
 // The reference's `Ell` (KIND = ELL_KIND_ELL, src/ell.rs) with its matrix in B200 HBM, or `EllStable`
@@ -105,6 +106,10 @@ class EllCudaT {
     // ---- pub fields of Ell (src/ell.rs:9-16)
     double kappa() const { double v; check(ellcuda_kappa(h_, &v)); return v; }
     Arr mq() const { Arr m(n_ * n_); check(ellcuda_get_mq(h_, m.data())); return m; }
+    // `pub no_defer_trick` is assigned after construction in the reference (src/ell.rs:342-344); so is the helper's
+    // `use_parallel_cut` (src/ell_calc.rs:630)
+    void set_no_defer_trick(bool on) { check(ellcuda_set_no_defer_trick(h_, on)); }
+    void set_use_parallel_cut(bool on) { check(ellcuda_set_use_parallel_cut(h_, on)); }
     std::size_t len() const { return n_; }
     ell_handle handle() const { return h_; }
 
@@ -115,7 +120,12 @@ class EllCudaT {
         d.mq = mq ? mq->data() : nullptr; d.diag = diag ? diag->data() : nullptr; d.xc = xc.data();
         d.no_defer_trick = cfg.no_defer_trick; d.use_parallel_cut = cfg.use_parallel_cut;
         d.row_begin = 0; d.row_end = static_cast<int64_t>(n_); d.reduce_mode = cfg.reduce_mode; d.stream = nullptr;
-        check(ellcuda_create(&d, &h_));
+        if (!cfg.devices.empty()) {
+            std::vector<int32_t> devs(cfg.devices.begin(), cfg.devices.end());
+            check(ellcuda_create_sharded(&d, static_cast<int32_t>(devs.size()), devs.data(), &h_));
+        } else {
+            check(ellcuda_create(&d, &h_));
+        }
     }
     template <class Cut> CutStatus update(int which, const std::pair<Arr, Cut>& cut) {
         if (cut.first.size() != n_) throw std::invalid_argument("grad must have n entries");  // assert_eq!(self.cols, x.len())

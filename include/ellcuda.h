@@ -162,7 +162,13 @@ typedef struct ell_batch_result { /* caller-allocated; optional members may be N
  * work is enqueued on desc->stream and the call returns without synchronising.          */
 int ellcuda_batch_solve(const ell_batch_desc* desc, const ell_batch_result* res);
 
-/* Number of kernels the last ellcuda_batch_solve on this thread launched (bench counter). */
+/* The same batch spread over `ndev` devices of this process (SURVEY.md §8b `ndev, devs`; SURVEY.md §8e: independent
+ * problems, contiguous blocks, no data-path collective).  Host buffers only (desc->on_device must be 0; desc->device and
+ * desc->stream are ignored): device r solves problems [r·count/ndev, (r+1)·count/ndev) on its own stream from its own host
+ * thread, and the call returns when every block's results are back in the caller's arrays.                            */
+int ellcuda_batch_solve_multi(const ell_batch_desc* desc, const ell_batch_result* res, int32_t ndev, const int32_t* devs);
+
+/* Number of kernels the last ellcuda_batch_solve(_multi) on this thread launched (bench counter). */
 int64_t ellcuda_last_launch_count(void);
 
 /* LowpassOracle::new's spectrum table (src/oracles/lowpass_oracle.rs:24-33 with
@@ -190,7 +196,11 @@ typedef struct ell_create_desc {
     int32_t device;
     int64_t n;
     double  kappa;             /* Ell::new_with_scalar(kappa,…) / new_with_matrix(kappa,…) */
-    const double* mq;          /* host, n·n row-major, symmetric; NULL ⇒ diag             */
+    const double* mq;          /* host, n·n row-major; NULL ⇒ diag.  Need not be symmetric: as in the reference
+                                  (src/ell.rs:31-41, 102, 117-128) the rows are used as given until the first
+                                  successful cut rewrites the upper triangle from the lower one; such a handle
+                                  keeps a second copy of the matrix until then and its ellcuda_update_finish
+                                  synchronises to learn the status                                           */
     const double* diag;        /* host, n; NULL ⇒ identity   (Ell::new: kappa=1, diag=val) */
     const double* xc;          /* host, n                                                 */
     int32_t no_defer_trick;
@@ -204,6 +214,15 @@ typedef struct ell_create_desc {
 } ell_create_desc;
 
 int  ellcuda_create(const ell_create_desc* desc, ell_handle* out); /* Ell::new* src/ell.rs:31-78 */
+/* The same Ell with its rows sharded over `ndev` devices of THIS process (SURVEY.md §8b `ndev, devs`): one slab per device,
+ * exchange blocks attached by pointer (peer access over NVLink), no launcher / torch / NCCL needed.  desc->device, row_begin,
+ * row_end and stream are ignored (each slab runs on its own stream); desc->reduce_mode applies to every slab (0 keeps the
+ * result bit-identical to the reference, k = ndev row segments keeps all SMs streaming).  The handle is used like any other:
+ * ellcuda_update (host gradient), update_begin/finish (the device gradient is copied to every slab's device and must be
+ * complete when begin is called), xc / set_xc / tsq / kappa / get_mq (all n rows) / dot_mv (all n entries) / clone / destroy.
+ * `devs` may name a device more than once (several slabs on one GPU, each on its own stream).                              */
+int  ellcuda_create_sharded(const ell_create_desc* desc, int32_t ndev, const int32_t* devs, ell_handle* out);
+int32_t ellcuda_group_size(ell_handle h);                          /* devices behind the handle (1 for a plain one)  */
 int  ellcuda_clone(ell_handle h, ell_handle* out);                 /* #[derive(Clone)] src/ell.rs:8 */
 void ellcuda_destroy(ell_handle h);                                /* Drop                     */
 
@@ -211,6 +230,12 @@ int ellcuda_xc(ell_handle h, double* out_n);              /* SearchSpace::xc   s
 int ellcuda_set_xc(ell_handle h, const double* x_n);      /* SearchSpace::set_xc      …:177-179   */
 int ellcuda_tsq(ell_handle h, double* out);               /* SearchSpace::tsq         …:149-151   */
 int ellcuda_kappa(ell_handle h, double* out);             /* pub field Ell::kappa     …:13        */
+/* The two public knobs the reference lets a caller change after construction:
+ *   Ell::no_defer_trick (pub field, src/ell.rs:10; written after new() at :342-344) — takes effect from the next update,
+ *   exactly as the field does (src/ell.rs:132-135 reads it at the end of update_core); Ell handles only;
+ *   EllCalc::use_parallel_cut (pub field of the helper, src/ell_calc.rs:630) — read by the next calc_* call.          */
+int ellcuda_set_no_defer_trick(ell_handle h, int32_t on);
+int ellcuda_set_use_parallel_cut(ell_handle h, int32_t on);
 int ellcuda_get_mq(ell_handle h, double* out_rows_by_n);  /* pub field Ell::mq (this slab's rows,
                                                              pending rank-1 applied first)        */
 

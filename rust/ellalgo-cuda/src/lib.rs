@@ -35,6 +35,11 @@ fn check(rc: i32) {
 
 impl<const KIND: i32> EllCudaT<KIND> {
     fn create(kappa: f64, mq: Option<&Arr>, diag: Option<&Arr>, xc: &Arr) -> Self {
+        Self::create_on(kappa, mq, diag, xc, &[])
+    }
+    /// `devices` non-empty: the rows of M are sharded over these GPUs of this process (`ellcuda_create_sharded`) — the
+    /// multi-GPU form of SURVEY §8b; the value is then used exactly like a single-GPU one.
+    fn create_on(kappa: f64, mq: Option<&Arr>, diag: Option<&Arr>, xc: &Arr, devices: &[i32]) -> Self {
         let n = xc.len();
         let desc = sys::ell_create_desc {
             kind: KIND,
@@ -53,8 +58,30 @@ impl<const KIND: i32> EllCudaT<KIND> {
             stream: std::ptr::null_mut(),
         };
         let mut h: sys::ell_handle = std::ptr::null_mut();
-        check(unsafe { sys::ellcuda_create(&desc, &mut h) });
+        if devices.is_empty() {
+            check(unsafe { sys::ellcuda_create(&desc, &mut h) });
+        } else {
+            check(unsafe { sys::ellcuda_create_sharded(&desc, devices.len() as i32, devices.as_ptr(), &mut h) });
+        }
         EllCudaT { h, n }
+    }
+    /// `Ell::new_with_scalar` with M row-sharded over `devices` (large n)
+    pub fn new_with_scalar_on(val: f64, xc: Arr, devices: &[i32]) -> Self {
+        Self::create_on(val, None, None, &xc, devices)
+    }
+    /// `Ell::new_with_matrix` with M row-sharded over `devices`
+    pub fn new_with_matrix_on(kappa: f64, mq: Arr, xc: Arr, devices: &[i32]) -> Self {
+        assert_eq!(mq.size(), xc.len() * xc.len());
+        Self::create_on(kappa, Some(&mq), None, &xc, devices)
+    }
+    /// the reference's `pub no_defer_trick` field is assigned after construction (src/ell.rs:10, 342-344):
+    /// `ell.no_defer_trick = true;` becomes `ell.set_no_defer_trick(true);`
+    pub fn set_no_defer_trick(&mut self, on: bool) {
+        check(unsafe { sys::ellcuda_set_no_defer_trick(self.h, on as i32) });
+    }
+    /// `helper.use_parallel_cut` (src/ell_calc.rs:630)
+    pub fn set_use_parallel_cut(&mut self, on: bool) {
+        check(unsafe { sys::ellcuda_set_use_parallel_cut(self.h, on as i32) });
     }
     /// src/ell.rs:31-41 / src/ell_stable.rs:18-27
     pub fn new_with_matrix(kappa: f64, mq: Arr, xc: Arr) -> Self {

@@ -36,6 +36,39 @@ for n, mode, xch in ((1024, 0, 'p2p'), (1000, 0, 'nccl'), (2048, 4, 'p2p'), (409
     r = s.state()
     ok &= bool(np.array_equal(slab, r["mq"][e.lo:e.hi]) if mode == 0 else np.abs(slab - r["mq"][e.lo:e.hi]).max() <= 1e-9)
     print(f"rank {rank}: n={n} mode={mode} exchange={xch} rows [{e.lo},{e.hi}) ok={ok}", flush=True)
+# the configuration bench.py times at this world size: n = 16384, reduce_mode = world, p2p — first two updates from M = I
+# against the checker (rank 0 runs it: ~15 s per update on one core), every rank compares its scalars, xc and its slab of M
+if os.environ.get("ELL_MGC_LARGE", "1") != "0":
+    import ctypes as C
+    n, mode = 16384, world
+    e = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local, exchange="p2p")
+    got = []
+    for k in range(2):
+        st = e.update(A.UPDATE_BIAS, torch.from_numpy(W.large_n_grad(n, k)).cuda(), ParallelCut(*W.LARGE_N_CUT))
+        got.append((int(st), e.tsq(), e.kappa, e.xc()))
+    slab = e.ell.mq
+    ref = [None]
+    if rank == 0:
+        mq, xc = np.eye(n), np.zeros(n)
+        kap, tsq = C.c_double(1.0), C.c_double(0.0)
+        states = []
+        for k in range(2):
+            g = W.large_n_grad(n, k)
+            st = R.lib().ellref_ell_update_inplace(n, mq.ctypes.data, xc.ctypes.data, C.byref(kap), C.byref(tsq), 0, 1, 0, g.ctypes.data,
+                                                   W.LARGE_N_CUT[0], 1, W.LARGE_N_CUT[1], None)
+            states.append((int(st), tsq.value, kap.value, xc.copy()))
+        bounds = [n * r // world for r in range(world + 1)]
+        ref = [(states, [mq[bounds[r]:bounds[r + 1]] for r in range(world)])]
+    dist.broadcast_object_list(ref, src=0)
+    states, slabs = ref[0]
+    worst = 0.0
+    for (st, t, kp, x), (st_r, t_r, kp_r, x_r) in zip(got, states):
+        ok &= st == st_r
+        worst = max(worst, abs(t - t_r) / abs(t_r), abs(kp - kp_r) / abs(kp_r), float(np.abs(x - x_r).max() / np.abs(x_r).max()))
+    worst = max(worst, float(np.abs(slab - slabs[rank]).max() / np.abs(slabs[rank]).max()))
+    ok &= worst <= 1e-9
+    print(f"rank {rank}: n={n} mode={mode} exchange=p2p (the bench configuration) max rel err {worst:.3g} ok={ok}", flush=True)
+    del e, slab, ref, slabs
 prob = W.bowl(1001, n=32, max_iters=300)
 prob.device = local
 out = solve_batch_sharded(prob, batch.solve_batch, rank, world)

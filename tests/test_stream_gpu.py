@@ -153,8 +153,10 @@ def test_use_parallel_cut_flag_and_clone(ref):
 
 def test_bad_arguments():
     from ellalgo_rs_b200._lib import EllCudaError
+    e = Ell(1.0, np.zeros(3), mq=np.arange(9.0).reshape(3, 3))      # non-symmetric: accepted, as Ell::new_with_matrix does
+    assert np.array_equal(e.mq, np.arange(9.0).reshape(3, 3))
     with pytest.raises(EllCudaError):
-        Ell(1.0, np.zeros(3), mq=np.arange(9.0).reshape(3, 3))      # asymmetric
+        Ell(1.0, np.zeros(3), device=99)
     with pytest.raises(ValueError):
         Ell(1.0, np.zeros(3), mq=np.eye(4))
     e = Ell.new_with_scalar(1.0, np.zeros(3))
