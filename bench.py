@@ -546,7 +546,7 @@ def main():
         rec, ni, es = timed_batch(hp, ("kappa0", "xc0", "diag0", "gamma0", "params"))
         rec["workload"] = "configs[1]: ProfitOracle (Cobb-Douglas, n=2), 2^20 independent instances per GPU, Ell::new([100,100],[0,0]), default Options"
         if cpu_ok:
-            rec["cpu_baseline"] = cpu_leg(lambda k: strided(hp, 16, k), 1 << 16, ni, es, 16)
+            rec["cpu_baseline"] = cpu_leg(lambda k: strided(hp, 1, k), c1, ni, es, 1)     # the whole batch: < 1 s on 16 threads
         extras["profit_1m"] = rec
         for name, general, cnt_l in (("lmi64_diag", False, 1 << 15), ("lmi64_general", True, 1 << 15)):
             hl = W.lmi(cnt_l, n=64, m=16, first=rank * cnt_l, general=general)
@@ -556,7 +556,8 @@ def main():
                                ("C4b EllStable::new_with_matrix (general LDL^T recurrence)" if general else
                                 "C4a EllStable::new_with_scalar (the factor provably stays diagonal)"))
             if cpu_ok:
-                rec["cpu_baseline"] = cpu_leg(lambda k, hl=hl: strided(hl, 16, k), 1 << 11, ni, es, 16)
+                st_, sm_ = (1, cnt_l) if general else (4, cnt_l // 4)     # C4b runs end after a few iterations: take them all
+                rec["cpu_baseline"] = cpu_leg(lambda k, hl=hl, st_=st_: strided(hl, st_, k), sm_, ni, es, st_)
             extras[name] = rec
 
     # ---------------------------------------------------------------- CPU baseline of the headline (rank 0, N=1 only)

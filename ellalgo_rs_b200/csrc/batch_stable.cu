@@ -20,148 +20,10 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "lmi_device.cuh"
 
 namespace ellcuda {
 namespace {
-
-constexpr int kNMax = 64;
-
-__device__ __forceinline__ int tri_index(int i, int j) {  // packed lower triangle, j <= i
-    return i * (i + 1) / 2 + j;
-}
-__device__ __forceinline__ int upper_off(int r, int n) {  // packed upper triangle incl. diagonal: row r starts here
-    return r * n - r * (r - 1) / 2;
-}
-__device__ __forceinline__ double bcast(double lo, double hi, int idx) {
-    const double a = __shfl_sync(0xffffffffu, lo, idx & 31);
-    const double b = __shfl_sync(0xffffffffu, hi, idx & 31);
-    return idx < 32 ? a : b;
-}
-
-struct WarpMem {
-    double* sx;    // n   xc (oracle input)
-    double* sv;    // n   general scratch vector (products / gg)
-    double* sw;    // n   w = inv(L) g
-    double* sz;    // n   z
-    double* sa;    // tri(m)  LMI elements A(i,j), j <= i
-    double* st;    // m*m LDLT storage
-    double* swit;  // m   witness
-    double* qu;    // GENERAL only: packed upper triangle of the EllStable matrix
-};
-
-// ---------------------------------------------------------------------------------------------- LMI oracle
-struct LmiShared {
-    const double* fp;  // n × fstride packed lower triangles of F_k
-    const double* bp;  // tri packed lower triangle of B
-    int fstride, m, tri, nvar;
-    int lmi0;          // LMI0Oracle (lmi0_oracle.rs:17-34): elements start from 0.0 and ADD F_k*x_k; gradient negated; no B
-};
-
-// returns true if a cut was produced: g0/g1 = this lane's gradient entries, ep = beta
-__device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, double& g0, double& g1, double& ep) {
-    const int m = L.m, tri = L.tri, n = L.nvar;
-    // --- elements A(i,j) = B[i][j] - sum_k F_k[i][j]*x[k], k ascending (src/oracles/lmi_oracle.rs:28-34)
-    // 5 elements per lane per pass: m = 16 (136 elements) is one pass with every lane busy (4 per lane needed a second
-    // pass with 8 active lanes: -900 instructions per call)
-    constexpr int U = 5;
-    for (int e0 = lane; e0 < tri; e0 += 32 * U) {
-        double a[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = e0 + 32 * u;
-            a[u] = (e < tri && !L.lmi0) ? L.bp[e] : 0.0;
-        }
-        if (!L.lmi0) {
-            for (int k = 0; k < n; ++k) {
-                const double xk = wm.sx[k];
-                const double* fk = L.fp + k * L.fstride;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = e0 + 32 * u;
-                    if (e < tri) a[u] -= fk[e] * xk;
-                }
-            }
-        } else {
-            for (int k = 0; k < n; ++k) {
-                const double xk = wm.sx[k];
-                const double* fk = L.fp + k * L.fstride;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = e0 + 32 * u;
-                    if (e < tri) a[u] += fk[e] * xk;
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = e0 + 32 * u;
-            if (e < tri) wm.sa[e] = a[u];
-        }
-    }
-    __syncwarp();
-    // --- LDLTMgr::factor (src/oracles/ldlt_mgr.rs:29-55); lane c follows column c of the current row
-    int pos = 0;
-    for (int i = 0; i < m; ++i) {
-        double acc = 0.0;                                   // s for column `lane`: sum_k T[i][k]*T[k][lane], k ascending
-        double diag = wm.sa[tri_index(i, 0)];               // get_elem(i, start)
-        for (int j = 0; j < i; ++j) {
-            const double d = __shfl_sync(0xffffffffu, diag, j);
-            const double val = d / wm.st[j * m + j];
-            if (lane == 0) {
-                wm.st[j * m + i] = d;                       // keep for later
-                wm.st[i * m + j] = val;                     // L[i][j]
-            }
-            const int c = lane;
-            if (c > j && c <= i) {
-                const double tjc = (c == i) ? d : wm.st[j * m + c];
-                acc += val * tjc;
-                if (c == j + 1) diag = wm.sa[tri_index(i, c)] - acc;   // get_elem(i, stop) - s
-            }
-        }
-        const double dii = __shfl_sync(0xffffffffu, diag, i);
-        if (lane == 0) wm.st[i * m + i] = dii;
-        __syncwarp();
-        if (dii <= 0.0) { pos = i + 1; break; }
-    }
-    if (pos == 0) return false;                             // is_spd
-    // --- witness (ldlt_mgr.rs:98-111), start = 0
-    const int mm = pos - 1;
-    if (lane == 0) wm.swit[mm] = 1.0;
-    __syncwarp();
-    for (int i = mm; i >= 1; --i) {
-        double s = 0.0;
-        for (int k = i; k < pos; ++k) s += wm.st[k * m + (i - 1)] * wm.swit[k];
-        __syncwarp();
-        if (lane == 0) wm.swit[i - 1] = -s;
-        __syncwarp();
-    }
-    ep = -wm.st[mm * m + mm];
-    // --- g[k] = sym_quad(F_k) (ldlt_mgr.rs:115-124): i outer, j inner, (wit[i]*F[i][j])*wit[j]
-    double r0 = 0.0, r1 = 0.0;
-    const int k0 = lane, k1 = lane + 32;
-    const double* f0 = L.fp + (k0 < n ? k0 : 0) * L.fstride;
-    const double* f1 = L.fp + (k1 < n ? k1 : 0) * L.fstride;
-    for (int i = 0; i < pos; ++i) {
-        const double wi = wm.swit[i];
-        int e = tri_index(i, 0);
-        for (int j = 0; j <= i; ++j, ++e) {          // F[i][j], j <= i: row i of the packed lower triangle
-            const double wj = wm.swit[j];
-            r0 += wi * f0[e] * wj;
-            r1 += wi * f1[e] * wj;
-        }
-        e = tri_index(i + 1, i);
-        for (int j = i + 1; j < pos; ++j) {           // F[i][j] = F[j][i], j > i: walk down column i
-            const double wj = wm.swit[j];
-            r0 += wi * f0[e] * wj;
-            r1 += wi * f1[e] * wj;
-            e += j + 1;
-        }
-    }
-    if (L.lmi0) { r0 = -r0; r1 = -r1; }   // g[k] = -sym_quad(F_k), lmi0_oracle.rs:31
-    g0 = k0 < n ? r0 : 0.0;
-    g1 = k1 < n ? r1 : 0.0;
-    return true;
-}
 
 // ---------------------------------------------------------------------------------------------- EllStable update
 // sequential sum of n values held as (lo, hi) per lane, via shared memory; every lane gets the result
@@ -263,27 +125,9 @@ __global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, i
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n, m = a.aux[0], tri = m * (m + 1) / 2;
-    // stage F_k (packed lower, odd stride) and B once per CTA
     double* fp = smem;
     double* bp = fp + (long long)n * fstride;
-    for (int idx = threadIdx.x; idx < n * tri; idx += blockDim.x) {
-        const int k = idx / tri, e = idx - k * tri;
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while (tri_index(i + 1, 0) <= e) ++i;
-        while (tri_index(i, 0) > e) --i;
-        const int j = e - tri_index(i, 0);
-        fp[k * fstride + e] = a.table[(long long)k * m * m + i * m + j];
-    }
-    for (int e = threadIdx.x; e < tri; e += blockDim.x) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while (tri_index(i + 1, 0) <= e) ++i;
-        while (tri_index(i, 0) > e) --i;
-        const int j = e - tri_index(i, 0);
-        bp[e] = lmi0 ? 0.0 : a.table[(long long)n * m * m + i * m + j];
-    }
-    __syncthreads();
-    long long base = (long long)n * fstride + tri;
-    base = (base + 1) & ~1LL;
+    const long long base = lmi_stage_tables(a, smem, fstride, lmi0);   // F_k (packed lower, odd stride) and B, once per CTA
     double* ws = smem + base + (long long)warp * per_warp_doubles;
     WarpMem wm;
     wm.sx = ws; wm.sv = ws + kNMax; wm.sw = ws + 2 * kNMax; wm.sz = ws + 3 * kNMax;
@@ -520,8 +364,9 @@ int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int s
     // LMI_OLD: the reference builds all m*m elements (k outermost) and then factorizes; every element undergoes the same
     // operations in the same order as in LMIOracle's lazy closure, so the lazy kernel is its exact equivalent.
     const int lmi0 = oracle_id == ELL_ORACLE_LMI0;
-    if (a.kind != ELL_KIND_ELLSTABLE || a.mode != ELL_MODE_FEAS) {
-        set_error("the LMI device oracle runs under cutting_plane_feas with EllStable");
+    if (a.kind == ELL_KIND_ELL) return launch_batch_ell64(a, oracle_id, s, sm_count, launches);   // the same oracles on Ell (M in TMEM)
+    if (a.mode != ELL_MODE_FEAS) {
+        set_error("the LMI device oracles run under cutting_plane_feas");
         return ELLCUDA_E_ARG;
     }
     const int n = a.n, m = a.aux[0];

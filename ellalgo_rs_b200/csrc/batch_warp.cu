@@ -417,7 +417,8 @@ int tuning_variant() {
 }  // namespace
 
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
-    if (a.n < 1 || a.n > 32) { set_error("warp-per-problem kernel needs 1 <= n <= 32"); return ELLCUDA_E_ARG; }
+    if (a.n > 32 && a.n <= 64 && a.kind == ELL_KIND_ELL) return launch_batch_ell64(a, oracle_id, s, sm_count, launches);   // M in TMEM
+    if (a.n < 1 || a.n > 64) { set_error("the batched Ell kernels need 1 <= n <= 64"); return ELLCUDA_E_ARG; }
     if (a.kind != ELL_KIND_ELL || a.mode != ELL_MODE_OPTIM) {
         set_error("warp-per-problem kernel: Ell + cutting_plane_optim only");
         return ELLCUDA_E_ARG;

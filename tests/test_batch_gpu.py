@@ -209,10 +209,10 @@ def test_empty_batch_and_bad_args(ref):
     from ellalgo_rs_b200._lib import EllCudaError
     with pytest.raises(EllCudaError):
         batch.solve_batch(BatchProblem(oracle_id=A.ORACLE_PROFIT, n=3, count=1, params=W.PROFIT_REF))
-    bad = W.bowl(2, n=4)
-    bad.mq0 = np.arange(16.0).reshape(4, 4)
-    with pytest.raises(EllCudaError):
-        batch.solve_batch(bad)
+    odd = W.bowl(2, n=4, max_iters=40)          # a non-symmetric new_with_matrix start is legal (src/ell.rs:31-41)
+    odd.mq0 = np.eye(4) + np.arange(16.0).reshape(4, 4) / 64.0
+    g, r = both(ref, odd)
+    assert_parity(g, r, exact=True, what="non-symmetric mq0")
 
 
 # ------------------------------------------------------------------ EllStable + LMI (n <= 64), warp per problem
