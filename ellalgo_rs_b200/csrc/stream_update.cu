@@ -105,37 +105,58 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ------------------------------------------------------------------------------------------------ kernels
 // Peer exchange (row-sharded handles attached with ellcuda_exchange_attach): the sweep CTA that completes a block of
-// 64 columns of grad_t stores it straight into EVERY rank's exchange block over NVLink (peer pointers); the last CTA
-// of the rank publishes the update's epoch in each peer's flag word; `finish_kernel` on every rank waits for all P
-// flags.  No collective call, no host involvement.  An exchange block holds two grad_t buffers (epoch parity) so
-// that a rank one update ahead never overwrites data a slower rank still reads.
+// 64 columns of grad_t stores it straight into EVERY rank's exchange block over NVLink (peer pointers) as flagged
+// 16-byte lines {lo32, epoch, hi32, epoch} — each 8-byte half carries its own flag and 8-byte stores are never torn,
+// so a reader that sees both flags equal to the update's epoch has the value (the "LL" scheme of collective
+// libraries).  There is no fence, no counter and no separate flag word on the path: one NVLink store latency after a
+// column block is summed, every rank can use it.  `finish_kernel` on every rank polls the n lines.  An exchange block
+// holds two line buffers (epoch parity) so that a rank one update ahead never overwrites data a slower rank still
+// reads.  No collective call, no host involvement.
 constexpr int kMaxRanks = 16;
 struct PeerTable {
     double* blk[kMaxRanks];   // rank r's exchange block (layout: xblk_* helpers below)
     int nranks;               // 0: no peer exchange (grad_t goes to this rank's buffer 0 only)
     int rank;
 };
-// exchange block, in doubles: grad_t[2][n] | flags[kMaxRanks] (u64, index = source rank) | omega_part[2][kMaxRanks]
-__host__ __device__ inline size_t xblk_doubles(long long n) { return (size_t)2 * n + kMaxRanks + 2 * kMaxRanks; }
-__host__ __device__ inline unsigned long long* xblk_flags(double* blk, long long n) {
-    return reinterpret_cast<unsigned long long*>(blk + 2 * n);
+// exchange block, in doubles: grad_t[n] plain (handles without peer exchange; ellcuda_grad_t_ptr) | pad to 16 bytes |
+// lines[2][n] of 16 bytes (peer exchange, buffer = epoch parity)
+__host__ __device__ inline size_t xblk_plain_doubles(long long n) { return (size_t)((n + 1) & ~1LL); }
+__host__ __device__ inline size_t xblk_doubles(long long n) { return xblk_plain_doubles(n) + (size_t)4 * n; }
+__host__ __device__ inline uint4* xblk_lines(double* blk, long long n, int parity) {
+    return reinterpret_cast<uint4*>(blk + xblk_plain_doubles(n)) + (long long)parity * n;
 }
-__host__ __device__ inline double* xblk_omega(double* blk, long long n, int parity) { return blk + 2 * n + kMaxRanks + parity * kMaxRanks; }
+__device__ __forceinline__ void ll_store(uint4* line, double v, unsigned flag) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+// polls until both halves of the line carry `flag`; false on timeout (~10 s) so that a lost peer cannot hang the GPU
+__device__ __forceinline__ bool ll_load(const uint4* line, unsigned flag, double& v) {
+    unsigned a, fa, b, fb;
+    long long t0 = 0;
+    for (int spins = 0;; ++spins) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(line) : "memory");
+        if (fa == flag && fb == flag) break;
+        if (spins == 64) t0 = clock64();
+        if (spins > 64) {
+            if (clock64() - t0 > 20000000000LL) return false;
+            __nanosleep(64);
+        }
+    }
+    v = __hiloint2double((int)b, (int)a);
+    return true;
+}
 
 struct SweepArgs {
     const double* g;           // gradient of this update, readable for npad rows (user buffer if n % 64 == 0, else a padded copy)
     const double2* pend;       // {grad_t[i], ratio·grad_t[i]} of the deferred rank-1 (written by finish), padded with zeros
     const Scal* sc;
     double* partial;           // nseg × ld_part column sums per row segment
-    double* block_omega;       // per column block: sum of g[c]·grad_t[c] over its 64 columns
     unsigned* cnt_block;       // arrivals per column block (self-resetting)
-    unsigned* cnt_all;         // column blocks completed (self-resetting)
     double* own_blk;           // this rank's exchange block
     double* out;               // non-null: plain GEMV — column sums go here (local column index), nothing else is published
     long long ld_part, n, w, c_glob0;
     int nseg;
     int exchange;              // 0: flush only (no grad_t is produced); 1: produce grad_t (+ push to peers if attached)
-    int omega_parts;           // 1: also publish this rank's part of omega (attached, reduce_mode > 0)
     PeerTable pt;
 };
 
@@ -188,39 +209,51 @@ __device__ __forceinline__ void tile_rows(double* __restrict__ tile_raw, const d
     }
 }
 
+// Programmatic dependent launch: a kernel launched with the attribute may start while its predecessor in the stream is still
+// running; everything before pdl_wait() must not touch what the predecessor writes.  pdl_trigger() lets the successor start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// shared-memory ring of one sweep warp: [kStages tiles][kStages pend rows][kStages g rows][kStages mbarriers]
+template <int kCols, int kRows, int kStages>
+struct Ring {
+    static constexpr int kTileBytes = kCols * kRows * 8;
+    static constexpr int kPendBytes = kRows * 16;
+    static constexpr int kGBytes = kRows * 8;
+    unsigned char *tiles, *pends, *gss;
+    unsigned long long* bars;
+    __device__ explicit Ring(unsigned char* smem_raw) {
+        tiles = smem_raw;
+        pends = smem_raw + kStages * kTileBytes;
+        gss = pends + kStages * kPendBytes;
+        bars = reinterpret_cast<unsigned long long*>(gss + kStages * kGBytes);
+    }
+    // a stage's barrier takes TWO arrivals per phase: the matrix tile and the vectors.  The tile of the first stages is
+    // requested before pdl_wait() (M is not written by the preceding finish kernel), their vectors after it.
+    __device__ __forceinline__ void issue_m(const CUtensorMap* map, int t, long long r0, long long c_loc0) const {
+        const int s = t % kStages;
+        mbar_expect_tx(&bars[s], kTileBytes);
+        tma_load_2d(tiles + s * kTileBytes, map, (int)c_loc0, (int)r0, &bars[s]);
+    }
+    template <bool PENDING>
+    __device__ __forceinline__ void issue_v(const SweepArgs& a, int t, long long r0) const {
+        const int s = t % kStages;
+        mbar_expect_tx(&bars[s], kGBytes + (PENDING ? kPendBytes : 0));
+        bulk_load_1d(gss + s * kGBytes, a.g + r0, kGBytes, &bars[s]);
+        if (PENDING) bulk_load_1d(pends + s * kPendBytes, a.pend + r0, kPendBytes, &bars[s]);
+    }
+};
+
 template <int kCols, int kRows, int kStages, bool PENDING, bool SCALE>
 __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepArgs& a, long long row_lo, long long row_hi, double scale,
-                                           unsigned char* smem_raw, double& acc0, double& acc1) {
+                                           const Ring<kCols, kRows, kStages>& ring, int ntiles, int pre, double& acc0, double& acc1) {
     constexpr int kTileBytes = kCols * kRows * 8;
     constexpr int kPendBytes = kRows * 16;
     constexpr int kGBytes = kRows * 8;
-    // smem: [kStages tiles][kStages pend rows][kStages g rows][kStages mbarriers]
-    unsigned char* tiles = smem_raw;
-    unsigned char* pends = smem_raw + kStages * kTileBytes;
-    unsigned char* gss = pends + kStages * kPendBytes;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(gss + kStages * kGBytes);
     const int lane = threadIdx.x;
     const long long c_loc0 = (long long)blockIdx.x * kCols;  // first local column of this warp's block
-    const int ntiles = (int)((row_hi - row_lo + kRows - 1) / kRows);
-
-    if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    auto issue = [&](int t) {  // lane 0 only
-        const int s = t % kStages;
-        const long long r0 = row_lo + (long long)t * kRows;
-        mbar_expect_tx(&bars[s], kTileBytes + kGBytes + (PENDING ? kPendBytes : 0));
-        tma_load_2d(tiles + s * kTileBytes, map, (int)c_loc0, (int)r0, &bars[s]);
-        bulk_load_1d(gss + s * kGBytes, a.g + r0, kGBytes, &bars[s]);
-        if (PENDING) bulk_load_1d(pends + s * kPendBytes, a.pend + r0, kPendBytes, &bars[s]);
-    };
-    if (lane == 0) {
-        const int pre = ntiles < (kStages - 1) ? ntiles : (kStages - 1);
-        for (int t = 0; t < pre; ++t) issue(t);
-    }
+    if (lane == 0)
+        for (int t = 0; t < pre; ++t) ring.template issue_v<PENDING>(a, t, row_lo + (long long)t * kRows);   // their tiles are on the way
 
     // this lane's column(s) (global indices) and their entries of the deferred rank-1 vectors
     constexpr int kPerLane = kCols == 64 ? 2 : 1;
@@ -235,10 +268,10 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % kStages;
-        mbar_wait(&bars[s], (unsigned)((t / kStages) & 1));
-        double* tile = reinterpret_cast<double*>(tiles + s * kTileBytes);
-        const double2* pd = reinterpret_cast<const double2*>(pends + s * kPendBytes);
-        const double* gs = reinterpret_cast<const double*>(gss + s * kGBytes);
+        mbar_wait(&ring.bars[s], (unsigned)((t / kStages) & 1));
+        double* tile = reinterpret_cast<double*>(ring.tiles + s * kTileBytes);
+        const double2* pd = reinterpret_cast<const double2*>(ring.pends + s * kPendBytes);
+        const double* gs = reinterpret_cast<const double*>(ring.gss + s * kGBytes);
         const long long r0 = row_lo + (long long)t * kRows;
         const int nrows = (int)((row_hi - r0) < kRows ? (row_hi - r0) : kRows);
         if (r0 + kRows <= blk_lo)
@@ -258,7 +291,9 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
             const int nt = t + kStages - 1;  // refill the stage whose store was issued one iteration ago
             if (nt < ntiles) {
                 if (PENDING) bulk_wait_read<1>();
-                issue(nt);
+                const long long rn = row_lo + (long long)nt * kRows;
+                ring.issue_m(map, nt, rn, c_loc0);
+                ring.template issue_v<PENDING>(a, nt, rn);
             }
         }
         __syncwarp();
@@ -276,13 +311,29 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     const long long row_lo = (long long)seg * rows_per;
     long long row_hi = row_lo + rows_per;
     if (row_hi > a.n) row_hi = a.n;
+    const Ring<kCols, kRows, kStages> ring(smem_raw);
+    const int ntiles = row_lo < row_hi ? (int)((row_hi - row_lo + kRows - 1) / kRows) : 0;
+    const int pre = ntiles < (kStages - 1) ? ntiles : (kStages - 1);
+    // ---- prologue, may overlap the preceding finish kernel (PDL): barriers, and the first tiles of M are requested.
+    // M is written only by sweeps of this handle, and the kernel before this one is never such a sweep still in flight
+    // (a finish kernel triggers its successor only after its own pdl_wait, i.e. after the previous sweep completed).
+    if (ntiles > 0) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) mbar_init(&ring.bars[s], 2);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int t = 0; t < pre; ++t) ring.issue_m(&map, t, row_lo + (long long)t * kRows, (long long)cb * kCols);
+        }
+        __syncwarp();
+    }
+    if (a.exchange) pdl_trigger();   // the finish kernel's CTAs may become resident now (a flush sweep keeps its successor out)
+    pdl_wait();                      // the preceding kernel (finish of the previous update, or whatever produced g) is complete
     double acc0 = 0.0, acc1 = 0.0;   // an empty segment contributes exact zeros
-    if (row_lo < row_hi) {
+    if (ntiles > 0) {
         const int pending = a.sc->pending;
         const double scale = a.sc->scale;
-        if (!pending) sweep_body<kCols, kRows, kStages, false, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
-        else if (scale == 1.0) sweep_body<kCols, kRows, kStages, true, false>(&map, a, row_lo, row_hi, 1.0, smem_raw, acc0, acc1);
-        else sweep_body<kCols, kRows, kStages, true, true>(&map, a, row_lo, row_hi, scale, smem_raw, acc0, acc1);
+        if (!pending) sweep_body<kCols, kRows, kStages, false, false>(&map, a, row_lo, row_hi, 1.0, ring, ntiles, pre, acc0, acc1);
+        else if (scale == 1.0) sweep_body<kCols, kRows, kStages, true, false>(&map, a, row_lo, row_hi, 1.0, ring, ntiles, pre, acc0, acc1);
+        else sweep_body<kCols, kRows, kStages, true, true>(&map, a, row_lo, row_hi, scale, ring, ntiles, pre, acc0, acc1);
     }
     if (!a.exchange) return;   // flush: only the deferred rank-1 was wanted
 
@@ -316,69 +367,27 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
         if (v1) a.out[cl + 1] = acc1;
         return;
     }
-    const unsigned long long epoch = a.sc->epoch;
-    const int attached = a.pt.nranks > 0;
-    if (attached && a.sc->failed) return;   // sticky peer failure: publish nothing, the peers' waits expire too
-    const long long off = (attached ? (long long)(epoch & 1ULL) * a.n : 0) + a.c_glob0 + cl;
-    if (!attached) {
-        if (v0) a.own_blk[off] = acc0;
-        if (v1) a.own_blk[off + 1] = acc1;
+    if (a.pt.nranks == 0) {   // no peer exchange: plain doubles (read by finish after this kernel, or gathered by the caller)
+        if (v0) a.own_blk[a.c_glob0 + cl] = acc0;
+        if (v1) a.own_blk[a.c_glob0 + cl + 1] = acc1;
         return;
     }
-    for (int r = 0; r < a.pt.nranks; ++r) {   // this block of grad_t, into every rank's buffer (NVLink stores)
-        if (v0) a.pt.blk[r][off] = acc0;
-        if (v1) a.pt.blk[r][off + 1] = acc1;
-    }
-    if (a.omega_parts) {   // this block's part of omega = sum g[c]*grad_t[c]: fixed order (lane pair, then xor tree)
-        double p = (v0 ? a.g[a.c_glob0 + cl] * acc0 : 0.0) + (v1 ? a.g[a.c_glob0 + cl + 1] * acc1 : 0.0);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (lane == 0) a.block_omega[cb] = p;
-    }
-    __threadfence_system();
-    __syncwarp();
-    unsigned done = 0;
-    if (lane == 0) done = atomicAdd(a.cnt_all, 1u);
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != gridDim.x - 1) return;
-    // the whole slab of this rank is out: publish (the warp that arrived last does it)
-    if (lane == 0) *a.cnt_all = 0;
-    __threadfence();
-    const int par = (int)(epoch & 1ULL);
-    if (a.omega_parts) {
-        double om = 0.0;   // block order, strictly sequential: deterministic.  Loads are coalesced, the adds walk the lanes.
-        for (unsigned base = 0; base < gridDim.x; base += 32) {
-            const unsigned b = base + lane;
-            const double v = b < gridDim.x ? __ldcg(a.block_omega + b) : 0.0;
-            const unsigned cnt = gridDim.x - base < 32 ? gridDim.x - base : 32;
-            for (unsigned j = 0; j < cnt; ++j) om += __shfl_sync(0xffffffffu, v, j);
-        }
-        if (lane < a.pt.nranks) xblk_omega(a.pt.blk[lane], a.n, par)[a.pt.rank] = om;
-    }
-    __threadfence_system();
-    __syncwarp();
-    if (lane < a.pt.nranks) {
-        unsigned long long* flag = xblk_flags(a.pt.blk[lane], a.n) + a.pt.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
-    }
-}
-
-// returns false on timeout (~10 s) so that a lost peer cannot hang the GPU
-__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long epoch) {
-    const long long t0 = clock64();
-    for (;;) {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-        if (v >= epoch) return true;
-        if (clock64() - t0 > 20000000000LL) return false;
-        __nanosleep(100);
+    if (a.sc->failed) return;   // sticky peer failure: publish nothing, the peers' waits expire too
+    const unsigned long long epoch = a.sc->epoch;
+    const unsigned flag = (unsigned)epoch;
+    const long long c = a.c_glob0 + cl;
+    for (int r = 0; r < a.pt.nranks; ++r) {   // this block of grad_t as flagged lines, into every rank's buffer (NVLink stores)
+        uint4* lines = xblk_lines(a.pt.blk[r], a.n, (int)(epoch & 1ULL));
+        if (v0) ll_store(lines + c, acc0, flag);
+        if (v1) ll_store(lines + c + 1, acc1, flag);
     }
 }
 
 // omega, tsq, EllCalc, xc, kappa, and the vectors of the next deferred rank-1 (src/ell.rs:103-115, 119, 130-135).
 // Identical on every rank.  A few CTAs: each one derives the scalars redundantly (same inputs, same order, same bits)
 // and updates its slice of xc / pend; the CTA that arrives last — when every other CTA has read `sc` — writes the new
-// scalars back, so no CTA can observe a half-updated state.
+// scalars back, so no CTA can observe a half-updated state.  With peer exchange grad_t is read from this rank's flagged
+// lines (polling until every slab has arrived), otherwise from the plain buffer the sweep (or the caller's allgather) filled.
 constexpr int kFinThreads = 1024;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)
 __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, double* blk, double* __restrict__ xc,
@@ -393,6 +402,8 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
     __shared__ Scal s_out;
     __shared__ double s_roo;
     const int tid = threadIdx.x;
+    pdl_wait();      // the sweep of this update is complete (its M stores too)
+    pdl_trigger();   // the next update's sweep may start its prologue: barriers and the first tiles of M
     if (tid == 0) {
         s_epoch = sc->epoch;
         s_kappa_in = sc->kappa;
@@ -400,64 +411,60 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
     }
     __syncthreads();
     const unsigned long long epoch = s_epoch;
-    const int par = nranks > 0 ? (int)(epoch & 1ULL) : 0;
-    const double* gt = blk + (long long)par * n;
-    if (nranks > 0 && !s_timeout) {   // peer exchange: all P slabs of grad_t must have landed in this rank's block
-        const unsigned long long* flags = xblk_flags(blk, n);
-        if (tid < nranks && !wait_flag(flags + tid, epoch)) {
-            s_timeout = 1;
-            atomicExch(&sc->failed, 1);   // one decision for the whole handle: the CTA that publishes re-reads it
-        }
-        __syncthreads();
-    }
-    if (!s_timeout) {
-        if (nranks > 0 && reduce_mode > 0) {
-            // every rank published its part of omega with its slab: sum the parts in rank order
-            if (tid == 0) {
-                const double* parts = xblk_omega(blk, n, par);
-                double acc = 0.0;
-                for (int r = 0; r < nranks; ++r) acc += __ldcg(parts + r);
-                s_omega = acc;
-            }
-        } else if (reduce_mode == 0) {
-            // grad.dot(&grad_t): products in parallel, the sum strictly left to right (src/arr.rs:443-451)
-            double acc = 0.0;
-            for (long long base = 0; base < n; base += kFinChunk) {
-                const int len = (int)((n - base) < kFinChunk ? (n - base) : kFinChunk);
-                for (int k = tid; k < len; k += kFinThreads) prod[k] = g[base + k] * __ldcg(gt + base + k);
-                __syncthreads();
-                if (tid == 0) {
-                    int k = 0;
-                    for (; k + 8 <= len; k += 8) {
-                        const double p0 = prod[k], p1 = prod[k + 1], p2 = prod[k + 2], p3 = prod[k + 3];
-                        const double p4 = prod[k + 4], p5 = prod[k + 5], p6 = prod[k + 6], p7 = prod[k + 7];
-                        acc += p0; acc += p1; acc += p2; acc += p3; acc += p4; acc += p5; acc += p6; acc += p7;
-                    }
-                    for (; k < len; ++k) acc += prod[k];
-                }
-                __syncthreads();
-            }
-            if (tid == 0) s_omega = acc;
-        } else {
-            // blocked: thread t sums elements t, t+1024, … in order, then a fixed binary tree — deterministic
-            double acc = 0.0;
-#pragma unroll 4
-            for (long long k = tid; k < n; k += kFinThreads) acc += g[k] * __ldcg(gt + k);
-            prod[tid] = acc;
+    const bool ll = nranks > 0;
+    const uint4* lines = ll ? xblk_lines(blk, n, (int)(epoch & 1ULL)) : nullptr;
+    const unsigned flag = (unsigned)epoch;
+    const bool dead = s_timeout != 0;
+    bool lost = false;   // this thread gave up on a line
+    auto load_gt = [&](long long k) -> double {
+        if (!ll) return __ldcg(blk + k);
+        double v = 0.0;
+        if (dead || lost) return v;
+        if (!ll_load(lines + k, flag, v)) lost = true;
+        return v;
+    };
+    if (reduce_mode == 0) {
+        // grad.dot(&grad_t): products in parallel, the sum strictly left to right (src/arr.rs:443-451)
+        double acc = 0.0;
+        for (long long base = 0; base < n; base += kFinChunk) {
+            const int len = (int)((n - base) < kFinChunk ? (n - base) : kFinChunk);
+            for (int k = tid; k < len; k += kFinThreads) prod[k] = g[base + k] * load_gt(base + k);
             __syncthreads();
-            for (int off = kFinThreads / 2; off > 0; off >>= 1) {
-                if (tid < off) prod[tid] = prod[tid] + prod[tid + off];
-                __syncthreads();
+            if (tid == 0) {
+                int k = 0;
+                for (; k + 8 <= len; k += 8) {
+                    const double p0 = prod[k], p1 = prod[k + 1], p2 = prod[k + 2], p3 = prod[k + 3];
+                    const double p4 = prod[k + 4], p5 = prod[k + 5], p6 = prod[k + 6], p7 = prod[k + 7];
+                    acc += p0; acc += p1; acc += p2; acc += p3; acc += p4; acc += p5; acc += p6; acc += p7;
+                }
+                for (; k < len; ++k) acc += prod[k];
             }
-            if (tid == 0) s_omega = prod[0];
+            __syncthreads();
         }
+        if (tid == 0) s_omega = acc;
+    } else {
+        // blocked: thread t sums elements t, t+1024, … in order, then a fixed binary tree — deterministic, the same on every rank
+        double acc = 0.0;
+#pragma unroll 4
+        for (long long k = tid; k < n; k += kFinThreads) acc += g[k] * load_gt(k);
+        prod[tid] = acc;
+        __syncthreads();
+        for (int off = kFinThreads / 2; off > 0; off >>= 1) {
+            if (tid < off) prod[tid] = prod[tid] + prod[tid + off];
+            __syncthreads();
+        }
+        if (tid == 0) s_omega = prod[0];
+    }
+    if (lost) {
+        s_timeout = 1;
+        atomicExch(&sc->failed, 1);   // one decision for the whole handle: the CTA that publishes re-reads it
     }
     __syncthreads();
     if (tid == 0) {
         Scal o;
         o.epoch = nranks > 0 ? epoch + 1 : epoch;
         o.kappa = s_kappa_in;
-        o.omega = 0.0; o.tsq = 0.0; o.ratio = 0.0; o.scale = 1.0; o.pending = 0; o.status = kUnknown;
+        o.omega = 0.0; o.tsq = 0.0; o.ratio = 0.0; o.scale = 1.0; o.pending = 0; o.status = kUnknown; o.failed = 0; o._pad = 0;
         s_roo = 0.0;
         if (!s_timeout) {
             const double omega = s_omega;
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         const long long hi = lo + per < n ? lo + per : n;
 #pragma unroll 4
         for (long long i = lo + tid; i < hi; i += kFinThreads) {
-            const double t = __ldcg(gt + i);
+            const double t = load_gt(i);                 // every line has arrived: no waiting here
             xc[i] -= roo * t;                            // src/ell.rs:111-115
             pend[i] = make_double2(t, ratio * t);        // r_qg = ratio * grad_t[i]  (src/ell.rs:119), applied by the next sweep
         }
@@ -597,7 +604,6 @@ struct ellcuda_ctx {
     double* xblk = nullptr;     // exchange block (IPC-shareable cudaMalloc): grad_t[2][n], flags, omega parts
     double2* pend = nullptr;    // npad + kColsMax + 2: deferred rank-1 vectors {grad_t, ratio·grad_t}
     double* partial = nullptr;  // nseg × ld_part
-    double* block_omega = nullptr;  // ncb
     unsigned* counters = nullptr;   // ncb (per column block) + 1 (blocks done) + 1 (finish CTAs arrived)
     ellcuda::Scal* sc = nullptr;
     int nranks = 0, rank = 0;                    // > 0 once ellcuda_exchange_attach* succeeded
@@ -630,13 +636,13 @@ namespace {
 
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
-    for (ellcuda_ctx* p : h->parts) free_ctx(p);
+    for (size_t r = h->parts.size(); r-- > 0;) free_ctx(h->parts[r]);   // reverse: a later slab may borrow an earlier one's stream
     h->parts.clear();
     DevGuard guard(h->device);
     cudaFree(h->A); cudaFree(h->ytmp);
     cudaFree(h->st_qu); cudaFree(h->st_scal); cudaFree(h->st_status);
     cudaFree(h->S); cudaFree(h->xc); cudaFree(h->gpad); cudaFree(h->gzero); cudaFree(h->gstage); cudaFreeHost(h->status_host);
-    cudaFree(h->pend); cudaFree(h->partial); cudaFree(h->block_omega); cudaFree(h->counters); cudaFree(h->sc);
+    cudaFree(h->pend); cudaFree(h->partial); cudaFree(h->counters); cudaFree(h->sc);
     for (int r = 0; r < kMaxRanks; ++r)
         if (h->peer_opened[r] && h->peer_blk[r]) cudaIpcCloseMemHandle(h->peer_blk[r]);
     cudaFree(h->xblk);
@@ -677,7 +683,6 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMalloc(&h->xblk, xblk_doubles(n) * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->pend, pend_n * 16));
     ELL_CUDA_TRY(cudaMalloc(&h->partial, (size_t)h->nseg * h->ld_part * 8));
-    ELL_CUDA_TRY(cudaMalloc(&h->block_omega, (size_t)h->ncb * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->counters, (size_t)(h->ncb + 2) * 4));
     ELL_CUDA_TRY(cudaMalloc(&h->sc, sizeof(Scal)));
     ELL_CUDA_TRY(cudaEventCreate(&h->ev0));
@@ -691,6 +696,9 @@ int alloc_ctx(ellcuda_ctx* h) {
     keep_mempool(h->device);
     return make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows, h->cols);
 }
+
+// ELLCUDA_PDL=0 switches programmatic dependent launch off (plain stream order between sweep and finish kernels)
+bool pdl_enabled() { return ELL_ENV_INT("ELLCUDA_PDL", 1) != 0; }
 
 template <int CO, int R, int ST>
 int launch_sweep_t(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {
@@ -707,7 +715,13 @@ int launch_sweep_t(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s
             if (h->device < 64) done_mask |= 1ULL << h->device;
         }
     }
-    sweep_kernel<CO, R, ST><<<grid, 32, smem, s>>>(h->asym_live ? h->mapA : h->map, a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: the prologue (barriers, first tiles of M) may
+    attr[0].val.programmaticStreamSerializationAllowed = 1;            // overlap the finish kernel of the previous update
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sweep_kernel<CO, R, ST>, h->asym_live ? h->mapA : h->map, a));
     return ELLCUDA_OK;
 }
 
@@ -740,11 +754,10 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev, double* plain_out = nullp
         h->launches += 1;
     }
     SweepArgs a;
-    a.g = h->gsrc; a.pend = h->pend; a.sc = h->sc; a.partial = h->partial; a.block_omega = h->block_omega;
-    a.cnt_block = h->counters; a.cnt_all = h->counters + h->ncb; a.own_blk = h->xblk; a.out = plain_out;
+    a.g = h->gsrc; a.pend = h->pend; a.sc = h->sc; a.partial = h->partial;
+    a.cnt_block = h->counters; a.own_blk = h->xblk; a.out = plain_out;
     a.ld_part = h->ld_part; a.n = h->n; a.w = h->w; a.c_glob0 = h->c0; a.nseg = h->nseg;
     a.exchange = flush ? 0 : 1;
-    a.omega_parts = (h->nranks > 0 && h->reduce_mode > 0) ? 1 : 0;
     a.pt.nranks = h->nranks; a.pt.rank = h->rank;
     for (int r = 0; r < kMaxRanks; ++r) a.pt.blk[r] = r < h->nranks ? h->peer_blk[r] : nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -931,9 +944,12 @@ int ellcuda_clone(ell_handle h, ell_handle* out) {
         g->reduce_mode = h->reduce_mode; g->no_defer = h->no_defer; g->use_parallel = h->use_parallel;
         for (ellcuda_ctx* p : h->parts) {
             ell_handle c = nullptr;
-            const int rc = ellcuda_clone(p, &c);
+            int rc = ellcuda_clone(p, &c);
             if (rc) { free_ctx(g); return rc; }
+            for (ellcuda_ctx* q : g->parts)   // slabs on one device share one stream (see ellcuda_create_sharded)
+                if (q->device == c->device) { rc = ellcuda_set_stream(c, q->stream); break; }
             g->parts.push_back(c);
+            if (rc) { free_ctx(g); return rc; }
         }
         const int rc = attach_group(g);
         if (rc) { free_ctx(g); return rc; }
@@ -1153,8 +1169,16 @@ int ellcuda_update_finish(ell_handle h) {
     const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
     long long fin_ctas = (h->n + kFinThreads - 1) / kFinThreads;
     if (fin_ctas > 16) fin_ctas = 16;
-    finish_kernel<<<(unsigned)fin_ctas, kFinThreads, 0, h->stream>>>(h->gsrc, h->xblk, h->xc, h->pend, h->sc, h->counters + h->ncb + 1,
-                                                                     h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode, h->nranks);
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)fin_ctas); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: resident while the sweep drains
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, finish_kernel, (const double*)h->gsrc, h->xblk, h->xc, h->pend, h->sc,
+                                        h->counters + h->ncb + 1, h->n, cc, h->which, h->cut, h->no_defer, h->reduce_mode, h->nranks));
+    }
     ELL_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     if (h->asym_live) {   // non-symmetric start: the host must learn of the first Success (see ellcuda_ctx::asym_live)
@@ -1328,8 +1352,10 @@ int ellcuda_create_sharded(const ell_create_desc* d, int32_t ndev, const int32_t
         dr.device = devs[r];
         dr.row_begin = r * base + (r < rem ? r : rem);
         dr.row_end = dr.row_begin + base + (r < rem ? 1 : 0);
-        dr.stream = nullptr;   // every slab runs on its own stream of its own device
-        ell_handle c = nullptr;
+        dr.stream = nullptr;   // every slab runs on its own stream of its own device ...
+        for (int q = 0; q < r; ++q)   // ... but slabs that share a device share ONE stream: a finish kernel waits for the other
+            if (devs[q] == devs[r]) { dr.stream = g->parts[q]->stream; break; }   // slabs' sweeps, and kernels that wait on one
+        ell_handle c = nullptr;       // another must never be separate launches that could run in either order on one GPU
         const int rc = ellcuda_create(&dr, &c);
         if (rc) { free_ctx(g); return rc; }
         g->parts.push_back(c);

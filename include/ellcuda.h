@@ -220,7 +220,8 @@ int  ellcuda_create(const ell_create_desc* desc, ell_handle* out); /* Ell::new* 
  * result bit-identical to the reference, k = ndev row segments keeps all SMs streaming).  The handle is used like any other:
  * ellcuda_update (host gradient), update_begin/finish (the device gradient is copied to every slab's device and must be
  * complete when begin is called), xc / set_xc / tsq / kappa / get_mq (all n rows) / dot_mv (all n entries) / clone / destroy.
- * `devs` may name a device more than once (several slabs on one GPU, each on its own stream).                              */
+ * `devs` may name a device more than once: the slabs of one GPU then share one stream, so that no kernel ever waits for a
+ * later launch on the same GPU.                                                                                           */
 int  ellcuda_create_sharded(const ell_create_desc* desc, int32_t ndev, const int32_t* devs, ell_handle* out);
 int32_t ellcuda_group_size(ell_handle h);                          /* devices behind the handle (1 for a plain one)  */
 int  ellcuda_clone(ell_handle h, ell_handle* out);                 /* #[derive(Clone)] src/ell.rs:8 */
