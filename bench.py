@@ -356,15 +356,15 @@ def main():
         # kappa shrinks by ~1.5 % per update, so after ~290 of these cuts tsq falls under beta1^2 and the cut degrades to
         # a single/failed cut (cheaper sweeps).  Every phase therefore starts from a fresh M = I and stays below 260.
 
-        def fresh(mode, warm=LARGE_WARMUP):
-            e = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local, exchange=args.exchange)
+        def fresh(mode, warm=LARGE_WARMUP, storage=0):
+            e = ShardedEll(1.0, np.zeros(n), reduce_mode=mode, device=local, exchange=args.exchange, storage=storage)
             for k in range(warm):
                 e.update_async(A.UPDATE_BIAS, grads[k % 20], cut)
             return e
 
-        def phases(mode):
+        def phases(mode, storage=0):
             """A: 200 updates as 10 replays of a 20-update CUDA graph; B: the sweep kernel alone (events around each launch)"""
-            ell = fresh(mode)
+            ell = fresh(mode, storage=storage)
             per_graph = 20
             graph = None if args.no_graph else ell.capture(A.UPDATE_BIAS, grads[:per_graph], cut, stream)
             barrier()
@@ -380,11 +380,11 @@ def main():
             a1.record(stream)
             barrier()
             t_large = max_over_ranks(a0.elapsed_time(a1) / 1e3)
-            l_launch = (2 * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
+            l_launch = ((3 if storage else 2) * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
             status = int(ell.ell.last_status())
             kind = ell.exchange_kind
             del graph, ell
-            ell = fresh(mode)
+            ell = fresh(mode, storage=storage)
             ell.ell.set_timing(True)
             sweeps = []
             for k in range(60):
@@ -398,10 +398,10 @@ def main():
                     "sweep_GBs_per_gpu": slab_bytes / (float(np.median(sweeps)) * 1e-3) / 1e9,
                     "last_status": status, "last_status_sweep_phase": status_b, "gpu_launches": int(l_launch), "exchange": kind}
 
-        def parity(mode):
+        def parity(mode, storage=0):
             """the first two updates from M = I on THIS configuration (n, reduce_mode, exchange, world) against the CPU checker
             (oracle/, ~15 s per update on one host core, rank 0); every rank compares its own scalars and xc, rank 0 its slab"""
-            ell = fresh(mode, warm=0)
+            ell = fresh(mode, warm=0, storage=storage)
             got = []
             for k in range(2):
                 ell.update_async(A.UPDATE_BIAS, grads[k], cut)
@@ -459,6 +459,18 @@ def main():
         parities = {str(mode): par}
         if world == 1 and not args.skip_cpu:
             parities["8"], _ = parity(8)
+        symmetric = None
+        if world == 1:
+            # tolerance-mode option: only the lower block-triangle is stored and streamed (8*n^2 bytes per update)
+            sp = phases(0, storage=1)
+            real = 8.0 * n * n + 8.0 * n * 64            # lower block-triangle incl. full diagonal tiles, read + write
+            symmetric = {"what": "ELL_STORAGE_SYMMETRIC: lower block-triangle of 64x64 tiles only; sums regrouped, results to 1e-9",
+                         "updates_per_s": sp["updates_per_s"], "ms_per_update": sp["ms_per_update"], "sweep_ms": sp["sweep_ms"],
+                         "bytes_per_update": real, "GBs": real * sp["updates_per_s"] / 1e9,
+                         "sweep_GBs": real / (sp["sweep_ms"] * 1e-3) / 1e9, "sweep_frac_of_measured_peak": real / (sp["sweep_ms"] * 1e-3) / 1e9 / peak,
+                         "last_status": sp["last_status"], "gpu_launches": sp["gpu_launches"]}
+            if not args.skip_cpu:
+                symmetric["parity"], _ = parity(0, storage=1)
         sweep_ms = main_phase["sweep_ms"]
         large = {
             "metric": "Ell::update HBM GB/s at n=16384 (whole job, 16*n^2 algorithmic bytes per update)",
@@ -468,6 +480,7 @@ def main():
             "last_status": main_phase["last_status"], "last_status_sweep_phase": main_phase["last_status_sweep_phase"],
             "gpu_launches": main_phase["gpu_launches"], "cuda_graph": not args.no_graph,
             "by_reduce_mode": by_mode,
+            "symmetric_storage": symmetric,
             "like_for_like": "N>1 runs reduce_mode=N (N ordered row segments per column block, 1e-9 gate); compare with "
                              "by_reduce_mode[str(N)] of the N=1 line, not with its bit-identical reduce_mode 0 headline",
             "parity": parities,

@@ -15,6 +15,7 @@ EXIT_NOSOLN, EXIT_NOEFFECT, EXIT_TOL, EXIT_MAXIT, EXIT_FEASIBLE = 1, 2, 4, 5, 6
 EXIT_NAMES = {1: "NoSoln", 2: "NoEffect", 4: "Tol", 5: "MaxIt", 6: "Feasible"}
 
 KIND_ELL, KIND_ELLSTABLE = 0, 1
+STORAGE_FULL, STORAGE_SYMMETRIC = 0, 1
 UPDATE_BIAS, UPDATE_CENTRAL, UPDATE_Q = 0, 1, 2
 MODE_OPTIM, MODE_FEAS, MODE_OPTIM_Q, MODE_BSEARCH = 0, 1, 2, 3
 
@@ -59,6 +60,6 @@ class CreateDesc(C.Structure):
         ("mq", C.c_void_p), ("diag", C.c_void_p), ("xc", C.c_void_p),
         ("no_defer_trick", C.c_int32), ("use_parallel_cut", C.c_int32),
         ("row_begin", C.c_int64), ("row_end", C.c_int64),
-        ("reduce_mode", C.c_int32), ("_pad0", C.c_int32),
+        ("reduce_mode", C.c_int32), ("storage", C.c_int32),
         ("stream", C.c_void_p),
     ]

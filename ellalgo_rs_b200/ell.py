@@ -34,7 +34,7 @@ class Ell:
     KIND = _abi.KIND_ELL
 
     def __init__(self, kappa, xc, mq=None, diag=None, *, device=0, no_defer_trick=False, use_parallel_cut=True,
-                 rows=None, reduce_mode=0, stream=0, devices=None, _handle=None):
+                 rows=None, reduce_mode=0, stream=0, devices=None, storage=0, _handle=None):
         """devices=[d0, d1, …]: rows sharded over these devices of this process (ellcuda_create_sharded); the object is
         then used exactly like a single-device one."""
         self._keep = []
@@ -59,6 +59,7 @@ class Ell:
         d.no_defer_trick, d.use_parallel_cut = int(no_defer_trick), int(use_parallel_cut)
         d.row_begin, d.row_end = (0, n) if rows is None else rows
         d.reduce_mode = reduce_mode
+        d.storage = storage          # 0 = full matrix (bit-identical), 1 = lower block-triangle only (half the traffic, 1e-9)
         d.stream = stream
         h = C.c_void_p()
         if devices is not None:

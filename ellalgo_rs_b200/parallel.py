@@ -53,7 +53,7 @@ class ShardedEll:
     into every peer's exchange block over NVLink and `finish` waits on device-side flags."""
 
     def __init__(self, kappa, xc, *, mq=None, diag=None, no_defer_trick=False, use_parallel_cut=True, reduce_mode=0,
-                 device=None, group=None, exchange="p2p"):
+                 device=None, group=None, exchange="p2p", storage=0):
         import torch
         import torch.distributed as dist
         from .ell import Ell
@@ -65,7 +65,7 @@ class ShardedEll:
         self.device = torch.cuda.current_device() if device is None else device
         self.lo, self.hi = shard_range(n, self.rank, self.world)
         self.ell = Ell(kappa, xc, mq=mq, diag=diag, device=self.device, no_defer_trick=no_defer_trick,
-                       use_parallel_cut=use_parallel_cut, rows=(self.lo, self.hi), reduce_mode=reduce_mode)
+                       use_parallel_cut=use_parallel_cut, rows=(self.lo, self.hi), reduce_mode=reduce_mode, storage=storage)
         # run on torch's current stream so that the NCCL exchange is ordered with the sweeps; torch reports the legacy
         # default stream as handle 0, which the C ABI reads as "own stream" — cudaStreamLegacy (0x1) names it explicitly
         self.ell.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)

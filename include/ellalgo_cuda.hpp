@@ -64,6 +64,7 @@ struct EllConfig {
     bool no_defer_trick = false;    // src/ell.rs:10
     bool use_parallel_cut = true;   // src/ell_calc.rs:630
     int reduce_mode = 0;            // 0 = bit-identical to the reference's summation order
+    int storage = ELL_STORAGE_FULL; // ELL_STORAGE_SYMMETRIC: lower block-triangle only, half the HBM traffic, results to 1e-9
     std::vector<int> devices;       // non-empty: rows sharded over these devices of this process (ellcuda_create_sharded)
 };
 
@@ -119,7 +120,7 @@ class EllCudaT {
         d.kind = KIND; d.device = cfg.device; d.n = static_cast<int64_t>(n_); d.kappa = kappa;
         d.mq = mq ? mq->data() : nullptr; d.diag = diag ? diag->data() : nullptr; d.xc = xc.data();
         d.no_defer_trick = cfg.no_defer_trick; d.use_parallel_cut = cfg.use_parallel_cut;
-        d.row_begin = 0; d.row_end = static_cast<int64_t>(n_); d.reduce_mode = cfg.reduce_mode; d.stream = nullptr;
+        d.row_begin = 0; d.row_end = static_cast<int64_t>(n_); d.reduce_mode = cfg.reduce_mode; d.storage = cfg.storage; d.stream = nullptr;
         if (!cfg.devices.empty()) {
             std::vector<int32_t> devs(cfg.devices.begin(), cfg.devices.end());
             check(ellcuda_create_sharded(&d, static_cast<int32_t>(devs.size()), devs.data(), &h_));

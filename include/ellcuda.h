@@ -56,6 +56,10 @@ extern "C" {
 #define ELL_KIND_ELL        0 /* src/ell.rs        */
 #define ELL_KIND_ELLSTABLE  1 /* src/ell_stable.rs */
 
+/* ---- storage of a single-instance Ell (ell_create_desc.storage) ------------------------- */
+#define ELL_STORAGE_FULL       0
+#define ELL_STORAGE_SYMMETRIC  1
+
 /* ---- which SearchSpace method — src/cutting_plane.rs:161-180 -------------------------- */
 #define ELL_UPDATE_BIAS     0 /* update_bias_cut    */
 #define ELL_UPDATE_CENTRAL  1 /* update_central_cut */
@@ -209,7 +213,11 @@ typedef struct ell_create_desc {
     int32_t reduce_mode;       /* 0: reference order (bit-identical grad_t and omega);
                                   k>0: each row sum split into k ordered segments and omega
                                   reduced blockwise — deterministic, ≤1e-13 rel. of mode 0 */
-    int32_t _pad0;
+    int32_t storage;           /* ELL_STORAGE_FULL (0): the full mirrored matrix as the reference holds it; results
+                                  bit-identical in reduce_mode 0.  ELL_STORAGE_SYMMETRIC (1): only the lower
+                                  block-triangle is kept and streamed — half the HBM traffic per update; the sums of
+                                  M·g are regrouped, so results are held to 1e-9 relative, not bit-identical.  Whole
+                                  matrix only (no row sharding), `mq` must be symmetric                          */
     void*   stream;            /* cudaStream_t; NULL ⇒ own stream, (void*)1 = cudaStreamLegacy */
 } ell_create_desc;
 

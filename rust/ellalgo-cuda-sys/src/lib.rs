@@ -56,7 +56,7 @@ pub struct ell_create_desc {
     pub row_begin: i64,
     pub row_end: i64,
     pub reduce_mode: i32,
-    pub _pad0: i32,
+    pub storage: i32, // ELL_STORAGE_FULL = 0 (bit-identical), ELL_STORAGE_SYMMETRIC = 1 (half the HBM traffic, 1e-9)
     pub stream: *mut c_void,
 }
 

@@ -54,7 +54,7 @@ impl<const KIND: i32> EllCudaT<KIND> {
             row_begin: 0,
             row_end: n as i64,
             reduce_mode: 0,
-            _pad0: 0,
+            storage: 0,
             stream: std::ptr::null_mut(),
         };
         let mut h: sys::ell_handle = std::ptr::null_mut();

@@ -254,3 +254,59 @@ def test_batch_solve_multi_bad_arguments():
     assert lib().ellcuda_batch_solve_multi(C.byref(d), C.byref(out), 1, devs) == A.E_ARG
     assert b"device" in lib().ellcuda_last_error()
     assert lib().ellcuda_batch_solve_multi(C.byref(d), C.byref(out), 0, devs) == A.E_ARG
+
+
+# ---------------------------------------------------------------- symmetric storage (lower block-triangle only), 1e-9 gate
+@pytest.mark.parametrize("n,start,mode", [(64, "scalar", 0), (100, "matrix", 0), (130, "diag", 3), (257, "matrix", 0), (700, "matrix", 2),
+                                          (1024, "scalar", 0), (33, "matrix", 1)])
+@pytest.mark.parametrize("no_defer", [False, True])
+def test_symmetric_storage_trajectory(ref, n, start, mode, no_defer):
+    kw = _start(n, start, n + 5)
+    e = Ell(kw["kappa"], kw["xc"], mq=kw.get("mq"), diag=kw.get("diag"), no_defer_trick=no_defer, storage=A.STORAGE_SYMMETRIC,
+            reduce_mode=mode)
+    s = ref.Space(A.KIND_ELL, n, kappa=kw["kappa"], mq=kw.get("mq"), diag=kw.get("diag"), xc=kw["xc"], no_defer_trick=no_defer)
+    r = s.state()
+    assert np.array_equal(e.mq, r["mq"])                  # packing / unpacking is exact
+    for k, (which, g, cut) in enumerate(_cuts(n, 12, n)):
+        st_g, st_r = _gpu_update(e, which, g, cut), _ref_update(s, which, g, cut)
+        r = s.state()
+        assert int(st_g) == st_r, f"step {k}: status"
+        assert rel_err(e.tsq(), r["tsq"]).max() <= REL_TOL and rel_err(e.kappa, r["kappa"]).max() <= REL_TOL, f"step {k}"
+        assert np.abs(e.xc() - r["xc"]).max() <= REL_TOL * np.abs(r["xc"]).max(), f"step {k}: xc"
+        if k in (3, 11):
+            assert np.abs(e.mq - r["mq"]).max() <= REL_TOL * np.abs(r["mq"]).max(), f"step {k}: mq"
+        if k == 5:
+            c, sc = e.clone(), s.clone()
+    which, g, cut = _cuts(n, 12, n)[6]
+    assert int(_gpu_update(c, which, g, cut)) == _ref_update(sc, which, g, cut)
+    assert np.abs(c.xc() - sc.state()["xc"]).max() <= REL_TOL * np.abs(sc.state()["xc"]).max()
+    x = np.random.default_rng(2).uniform(-1, 1, n)        # Arr::dot_mv on the packed matrix
+    y = np.zeros(n)
+    m = np.ascontiguousarray(r["mq"])
+    ref.lib().ellref_dot_mv(m.ctypes.data, x.ctypes.data, n, n, y.ctypes.data)
+    assert np.abs(e.dot_mv(x) - y).max() <= REL_TOL * np.abs(y).max()
+
+
+def test_symmetric_storage_is_deterministic_and_rejects_what_it_cannot_do():
+    n = 300
+    kw = _start(n, "matrix", 1)
+    runs = []
+    for _ in range(2):
+        e = Ell(kw["kappa"], kw["xc"], mq=kw["mq"], storage=A.STORAGE_SYMMETRIC)
+        for which, g, cut in _cuts(n, 6, 3):
+            _gpu_update(e, which, g, cut)
+        runs.append((e.tsq(), e.kappa, e.xc(), e.mq))
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1]
+    assert np.array_equal(runs[0][2], runs[1][2]) and np.array_equal(runs[0][3], runs[1][3])
+    with pytest.raises(EllCudaError):
+        Ell(1.0, np.zeros(4), mq=_asym(4, 0), storage=A.STORAGE_SYMMETRIC)       # needs a symmetric matrix
+    with pytest.raises(EllCudaError):
+        Ell(1.0, np.zeros(128), rows=(0, 64), storage=A.STORAGE_SYMMETRIC)        # does not shard rows
+
+
+def test_symmetric_storage_drives_the_reference_loop():  # src/example1.rs:39-70 → 25 iterations, through the packed matrix
+    from ellalgo_rs_b200.cutting_plane import Options, cutting_plane_optim
+    from test_stream_gpu import _Example1
+    e = Ell.new_with_scalar(10.0, np.zeros(2), storage=A.STORAGE_SYMMETRIC)
+    xbest, niter, gamma = cutting_plane_optim(_Example1(), e, -math.inf, Options(tolerance=1e-10))
+    assert xbest is not None and niter == 25
