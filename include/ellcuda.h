@@ -196,7 +196,12 @@ typedef struct ell_create_desc {
                                   factor as the reference holds it (diagonal + strict upper triangle are
                                   read; need not be symmetric); its triangular recurrences neither stream
                                   nor shard (one warp for n <= 64, one CTA above; serial in the reference's
-                                  summation order) — throughput comes from ellcuda_batch_solve           */
+                                  summation order) — throughput comes from ellcuda_batch_solve.
+                                  Cost of one update_core on a B200: ~25 us at n = 100, ~0.7 ms at n = 512,
+                                  ~2.7 ms at n = 1024, ~11 ms at n = 2048: the back substitution is one chain of
+                                  n^2/2 dependent FP64 subtractions (10 clocks each) because the reference sums
+                                  each row left to right starting from the entry that finished last.  The
+                                  batched EllStable kernel runs 7.9e7 such updates/s at n = 64 (DIAG start)     */
     int32_t device;
     int64_t n;
     double  kappa;             /* Ell::new_with_scalar(kappa,…) / new_with_matrix(kappa,…) */
