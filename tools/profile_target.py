@@ -21,3 +21,19 @@ if what in ("all", "stream"):
         e.update_begin(A.UPDATE_BIAS, gs[k % 4].data_ptr(), ParallelCut(*W.LARGE_N_CUT)); e.update_finish()
     e.sync()
     print("large-n status", e.last_status(), e.kappa)
+
+if what == "headline":   # the bench's launch shape: 65536 lowpass problems, one launch
+    t = batch.lowpass_table(32)
+    o = batch.solve_batch(W.lowpass(65536, t))
+    print("lowpass iterations", int(o.num_iters.sum()) + int((o.exit_status != 5).sum()))
+if what == "sym":        # symmetric storage, n = 16384: a few updates
+    n = 16384
+    e = Ell.new_with_scalar(1.0, np.zeros(n), storage=A.STORAGE_SYMMETRIC)
+    gs = [torch.from_numpy(W.large_n_grad(n, k)).cuda() for k in range(4)]
+    for k in range(5):
+        e.update_begin(A.UPDATE_BIAS, gs[k % 4].data_ptr(), ParallelCut(*W.LARGE_N_CUT)); e.update_finish()
+    e.sync()
+    print("sym status", e.last_status(), e.kappa)
+if what == "lmi":
+    o = batch.solve_batch(W.lmi(1 << 15, n=64, m=16))
+    print("lmi iterations", int(o.num_iters.sum()) + int((o.exit_status != 5).sum()))
