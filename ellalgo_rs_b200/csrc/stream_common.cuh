@@ -123,17 +123,19 @@ __device__ __forceinline__ bool ll_load(const uint4* line, unsigned flag, double
 // MODE 0: every row of the tile is above the block's columns (i < c):   update = (ratio·gt[c]) · gt[i]
 // MODE 1: every row is at or below them (i >= c):                        update = (ratio·gt[i]) · gt[c]
 // MODE 2: the tile crosses the diagonal: choose per element.             (src/ell.rs:118-127: hi = max, lo = min)
-template <int COLS, int MODE, bool PENDING, bool SCALE>
+// STRIDE = doubles per tile row, PERLANE = columns per lane: a 64-wide tile is walked either by one warp with two columns per
+// lane (16-byte accesses) or by two warps with one column per lane each (the second warp's base pointer is 32 columns in).
+template <int COLS, int MODE, bool PENDING, bool SCALE, int STRIDE = COLS, int PERLANE = (COLS == 64 ? 2 : 1)>
 __device__ __forceinline__ void tile_rows(double* __restrict__ tile_raw, const double* __restrict__ gs, const double2* __restrict__ pd,
                                           int lane, int nrows, int row0, int col0, double gt_c0, double gt_c1, double rg_c0,
                                           double rg_c1, double scale, double& acc0, double& acc1) {
-    constexpr bool TWO = COLS == 64;                     // two columns per lane (16-byte accesses) or one
+    constexpr bool TWO = PERLANE == 2;                   // two columns per lane (16-byte accesses) or one
     if (COLS < 32 && lane >= COLS) return;               // 16-column blocks: the upper half-warp has no column
 #pragma unroll 8
     for (int r = 0; r < nrows; ++r) {  // nrows < tile height only in the last tile of a segment (rows past n are not M)
         double2 m;
-        if (TWO) m = reinterpret_cast<double2*>(tile_raw)[r * (COLS / 2) + lane];
-        else { m.x = tile_raw[r * COLS + lane]; m.y = 0.0; }
+        if (TWO) m = reinterpret_cast<double2*>(tile_raw)[r * (STRIDE / 2) + lane];
+        else { m.x = tile_raw[r * STRIDE + lane]; m.y = 0.0; }
         const double gi = gs[r];       // broadcast
         if (PENDING) {
             const double2 p = pd[r];   // broadcast: {gt[i], ratio*gt[i]}
@@ -155,8 +157,8 @@ __device__ __forceinline__ void tile_rows(double* __restrict__ tile_raw, const d
                 m.x *= scale;  // mq *= kappa   (src/ell.rs:132-135)
                 if (TWO) m.y *= scale;
             }
-            if (TWO) reinterpret_cast<double2*>(tile_raw)[r * (COLS / 2) + lane] = m;
-            else tile_raw[r * COLS + lane] = m.x;
+            if (TWO) reinterpret_cast<double2*>(tile_raw)[r * (STRIDE / 2) + lane] = m;
+            else tile_raw[r * STRIDE + lane] = m.x;
         }
         acc0 += m.x * gi;  // grad_t[c] += M[i][c] * g[i], i ascending
         if (TWO) acc1 += m.y * gi;

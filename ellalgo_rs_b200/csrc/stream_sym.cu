@@ -10,7 +10,7 @@
 // reference (tests hold them to that), not bit-identical.  The deferred rank-1 of the previous cut is applied to the tile in
 // the same pass (src/ell.rs:117-128: element (i,j), i >= j, -= (ratio·g̃[i])·g̃[j]), diagonal tiles keep both triangles.
 //
-// Work split: one warp per (pair of column blocks, row segment): column block J has T−J tiles, so J is paired with T−1−J
+// Work split: one CTA of two warps per (pair of column blocks, row segment): column block J has T−J tiles, so J is paired with T−1−J
 // (T+1 tiles per pair) and the pair's tile list is cut into `nseg` contiguous chunks.  Tiles are contiguous 32 KB blocks:
 // 1-D bulk copies (cp.async.bulk) through a 3-stage mbarrier ring, updated in place, stored back by bulk copy.
 #include <algorithm>
@@ -83,11 +83,15 @@ struct Chunk {   // this warp's part of its pair's tile list
     }
 };
 
+// Two warps per CTA: in pass 1 warp w owns columns 32w..32w+31 of the tile (one per lane, rows ascending), in pass 2 rows
+// 32w..32w+31 (one per lane).  With a single warp the tile cost 1730 dependent instructions at ~3.5 clocks each = 3 us against
+// 2.7 us of HBM time per tile (ncu: 28 % issue active, 71 % of the copy bandwidth); split over two warps it is well below.
 template <bool PENDING, bool SCALE>
 __device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, const Chunk& ch, int pre, double scale) {
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lcol = 32 * wid + lane;   // this thread's column in pass 1, row in pass 2
     const int seg = blockIdx.y;
-    if (lane == 0)
+    if (threadIdx.x == 0)
         for (int t = 0; t < pre; ++t) {
             int I, J;
             ch.tile_of(t, I, J);
@@ -95,27 +99,26 @@ __device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, 
         }
     double* cp = a.colpart + (long long)seg * a.npad;
     if (a.exchange) {   // a slot the chunk does not reach must still read as zero in the combine
-        *reinterpret_cast<double2*>(cp + (long long)ch.Ja * kTile + 2 * lane) = make_double2(0.0, 0.0);
-        *reinterpret_cast<double2*>(cp + (long long)ch.Jb * kTile + 2 * lane) = make_double2(0.0, 0.0);
+        cp[(long long)ch.Ja * kTile + lcol] = 0.0;
+        cp[(long long)ch.Jb * kTile + lcol] = 0.0;
     }
     int curJ = -1;
-    double acc0 = 0.0, acc1 = 0.0, gt_c0 = 0.0, gt_c1 = 0.0, rg_c0 = 0.0, rg_c1 = 0.0;
+    double acc = 0.0, unused = 0.0, gt_c = 0.0, rg_c = 0.0;
     for (int t = 0; t < ch.ntiles; ++t) {
         int I, J;
         ch.tile_of(t, I, J);
         if (J != curJ) {   // a new column block (at most once per chunk after the first tile)
-            if (curJ >= 0 && a.exchange) *reinterpret_cast<double2*>(cp + (long long)curJ * kTile + 2 * lane) = make_double2(acc0, acc1);
+            if (curJ >= 0 && a.exchange) cp[(long long)curJ * kTile + lcol] = acc;
             curJ = J;
-            acc0 = 0.0; acc1 = 0.0;
-            const long long c = (long long)J * kTile + 2 * lane;
+            acc = 0.0;
+            const long long c = (long long)J * kTile + lcol;
             if (PENDING) {
-                const double2 p0 = a.pend[c], p1 = a.pend[c + 1];
-                gt_c0 = p0.x; rg_c0 = p0.y;
-                gt_c1 = p1.x; rg_c1 = p1.y;
+                const double2 p0 = a.pend[c];
+                gt_c = p0.x; rg_c = p0.y;
             }
-            __syncwarp();
-            *reinterpret_cast<double2*>(ring.gcol + 2 * lane) = *reinterpret_cast<const double2*>(a.g + c);   // g of the columns (row sums)
-            __syncwarp();
+            __syncthreads();
+            ring.gcol[lcol] = a.g[c];   // g of the columns (row sums)
+            __syncthreads();
         }
         const int s = t % kSymStages;
         mbar_wait(&ring.bars[s], (unsigned)((t / kSymStages) & 1));
@@ -123,29 +126,24 @@ __device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, 
         const double2* pd = reinterpret_cast<const double2*>(ring.pends + s * kPendBytes);
         const double* gs = reinterpret_cast<const double*>(ring.gss + s * kVecBytes);
         // pass 1: the deferred rank-1 in place, and the column sums (rows ascending)
-        if (I == J) tile_rows<kTile, 2, PENDING, SCALE>(tile, gs, pd, lane, kTile, 0, 2 * lane, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
-        else tile_rows<kTile, 1, PENDING, SCALE>(tile, gs, pd, lane, kTile, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
+        if (I == J) tile_rows<kTile, 2, PENDING, SCALE, kTile, 1>(tile + 32 * wid, gs, pd, lane, kTile, 0, lcol, gt_c, 0.0, rg_c, 0.0, scale, acc, unused);
+        else tile_rows<kTile, 1, PENDING, SCALE, kTile, 1>(tile + 32 * wid, gs, pd, lane, kTile, 0, 0, gt_c, 0.0, rg_c, 0.0, scale, acc, unused);
         if (I != J && a.exchange) {
-            // pass 2: the tile also stands for M[c][i] of the upper triangle: row sums against g of the column block.  Lane L takes
-            // rows L and L+32 and walks the columns from L on (mod 64), so that a half-warp always touches 16 different banks.
-            if (PENDING) __syncwarp();
-            double r0 = 0.0, r1 = 0.0;
-            const double* row0 = tile + lane * kTile;
-            const double* row1 = tile + (lane + 32) * kTile;
+            // pass 2: the tile also stands for M[c][i] of the upper triangle: row sums against g of the column block.  Thread q takes
+            // row q and walks the columns from its lane on (mod 64), so that a half-warp always touches 16 different banks.
+            if (PENDING) __syncthreads();
+            double r0 = 0.0;
+            const double* row = tile + lcol * kTile;
 #pragma unroll 8
             for (int c = 0; c < kTile; ++c) {
                 const int cc = (c + lane) & (kTile - 1);
-                const double gc = ring.gcol[cc];
-                r0 += row0[cc] * gc;
-                r1 += row1[cc] * gc;
+                r0 += row[cc] * ring.gcol[cc];
             }
-            double* rp = a.rowpart + (long long)J * a.npad + (long long)I * kTile;
-            rp[lane] = r0;
-            rp[lane + 32] = r1;
+            a.rowpart[(long long)J * a.npad + (long long)I * kTile + lcol] = r0;
         }
         if (PENDING) fence_async_smem();  // generic-proxy writes -> visible to the bulk store
-        __syncwarp();
-        if (lane == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
             if (PENDING) {
                 bulk_store_1d(a.Mp + tile_index(I, J) * kTileDoubles, tile, kTileBytes);
                 bulk_commit();
@@ -159,16 +157,14 @@ __device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, 
                 ring.issue_v<PENDING>(a, nt, In);
             }
         }
-        __syncwarp();
     }
-    if (curJ >= 0 && a.exchange) *reinterpret_cast<double2*>(cp + (long long)curJ * kTile + 2 * lane) = make_double2(acc0, acc1);
-    if (PENDING && lane == 0) bulk_wait_all();
+    if (curJ >= 0 && a.exchange) cp[(long long)curJ * kTile + lcol] = acc;
+    if (PENDING && threadIdx.x == 0) bulk_wait_all();
 }
 
-// grid = (pairs of column blocks, row segments); block = 32 threads
-__global__ void __launch_bounds__(32) sym_sweep_kernel(const SymArgs a) {
+// grid = (pairs of column blocks, row segments); block = 64 threads
+__global__ void __launch_bounds__(64) sym_sweep_kernel(const SymArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
     const SymRing ring(smem_raw);
     Chunk ch;
     ch.Ja = blockIdx.x;
@@ -182,7 +178,7 @@ __global__ void __launch_bounds__(32) sym_sweep_kernel(const SymArgs a) {
     if (ch.ntiles < 0) ch.ntiles = 0;
     const int pre = ch.ntiles < (kSymStages - 1) ? ch.ntiles : (kSymStages - 1);
     // prologue (may overlap the preceding finish kernel, see stream_update.cu): barriers and the first tiles of M
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         for (int s = 0; s < kSymStages; ++s) mbar_init(&ring.bars[s], 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int t = 0; t < pre; ++t) {
@@ -191,7 +187,7 @@ __global__ void __launch_bounds__(32) sym_sweep_kernel(const SymArgs a) {
             ring.issue_m(a, t, I, J);
         }
     }
-    __syncwarp();
+    __syncthreads();
     if (a.exchange) pdl_trigger();
     pdl_wait();
     const int pending = a.sc->pending;
@@ -308,7 +304,7 @@ int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_o
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((h->T + 1) / 2), (unsigned)h->sym_nseg); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = kSymSmem; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)((h->T + 1) / 2), (unsigned)h->sym_nseg); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = kSymSmem; cfg.stream = s;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
     ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sym_sweep_kernel, a));
     h->launches += 1;

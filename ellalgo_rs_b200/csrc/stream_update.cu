@@ -88,20 +88,32 @@ struct Ring {
     }
 };
 
-template <int kCols, int kRows, int kStages, bool PENDING, bool SCALE>
+// kW = warps per CTA.  One warp (two columns per lane) is what the narrow column blocks and small matrices use; with two warps
+// each lane owns ONE column (warp w: columns 32w..32w+31 of the block), which halves the dependent instruction stream per
+// tile: ncu showed the single warp issuing 18 % of the time with the rest spent on its own dependencies, i.e. 2.2 us of
+// instruction latency per 32 KB tile against 2.56 us of HBM time — two warps put the tile's work well under its HBM time.
+// The sums are still per column, rows ascending: bit-identical.
+template <int kW>
+__device__ __forceinline__ void cta_sync() {
+    if (kW == 1) __syncwarp();
+    else __syncthreads();
+}
+
+template <int kCols, int kRows, int kStages, int kW, bool PENDING, bool SCALE>
 __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepArgs& a, long long row_lo, long long row_hi, double scale,
                                            const Ring<kCols, kRows, kStages>& ring, int ntiles, int pre, double& acc0, double& acc1) {
     constexpr int kTileBytes = kCols * kRows * 8;
     constexpr int kPendBytes = kRows * 16;
     constexpr int kGBytes = kRows * 8;
-    const int lane = threadIdx.x;
-    const long long c_loc0 = (long long)blockIdx.x * kCols;  // first local column of this warp's block
-    if (lane == 0)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long c_loc0 = (long long)blockIdx.x * kCols;  // first local column of this CTA's block
+    if (threadIdx.x == 0)
         for (int t = 0; t < pre; ++t) ring.template issue_v<PENDING>(a, t, row_lo + (long long)t * kRows);   // their tiles are on the way
 
     // this lane's column(s) (global indices) and their entries of the deferred rank-1 vectors
-    constexpr int kPerLane = kCols == 64 ? 2 : 1;
-    const long long cg0 = a.c_glob0 + c_loc0 + kPerLane * (kCols < 32 ? (lane % kCols) : lane);
+    constexpr int kPerLane = (kCols == 64 && kW == 1) ? 2 : 1;
+    const int lcol = kW == 2 ? 32 * wid + lane : kPerLane * (kCols < 32 ? (lane % kCols) : lane);   // column inside the block
+    const long long cg0 = a.c_glob0 + c_loc0 + lcol;
     double gt_c0 = 0.0, gt_c1 = 0.0, rg_c0 = 0.0, rg_c1 = 0.0;
     if (PENDING) {
         const double2 p0 = a.pend[cg0], p1 = a.pend[cg0 + 1];  // pend is padded, always readable
@@ -118,16 +130,17 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
         const double* gs = reinterpret_cast<const double*>(ring.gss + s * kGBytes);
         const long long r0 = row_lo + (long long)t * kRows;
         const int nrows = (int)((row_hi - r0) < kRows ? (row_hi - r0) : kRows);
+        double* base = kW == 2 ? tile + 32 * wid : tile;
         if (r0 + kRows <= blk_lo)
-            tile_rows<kCols, 0, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
+            tile_rows<kCols, 0, PENDING, SCALE, kCols, kPerLane>(base, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
         else if (r0 >= blk_hi - 1)
-            tile_rows<kCols, 1, PENDING, SCALE>(tile, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
+            tile_rows<kCols, 1, PENDING, SCALE, kCols, kPerLane>(base, gs, pd, lane, nrows, 0, 0, gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
         else
-            tile_rows<kCols, 2, PENDING, SCALE>(tile, gs, pd, lane, nrows, (int)(r0 - blk_lo), kPerLane * lane, gt_c0, gt_c1, rg_c0, rg_c1,
-                                         scale, acc0, acc1);
+            tile_rows<kCols, 2, PENDING, SCALE, kCols, kPerLane>(base, gs, pd, lane, nrows, (int)(r0 - blk_lo), kW == 2 ? lcol : kPerLane * lane,
+                                                                gt_c0, gt_c1, rg_c0, rg_c1, scale, acc0, acc1);
         if (PENDING) fence_async_smem();  // generic-proxy writes -> visible to the TMA store
-        __syncwarp();
-        if (lane == 0) {
+        cta_sync<kW>();
+        if (threadIdx.x == 0) {
             if (PENDING) {
                 tma_store_2d(map, (int)c_loc0, (int)r0, tile);
                 bulk_commit();
@@ -140,16 +153,17 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
                 ring.template issue_v<PENDING>(a, nt, rn);
             }
         }
-        __syncwarp();
+        if (kW == 1) __syncwarp();
     }
-    if (PENDING && lane == 0) bulk_wait_all();
+    if (PENDING && threadIdx.x == 0) bulk_wait_all();
 }
 
-// grid = (column blocks, row segments); block = 32 threads.
-template <int kCols, int kRows, int kStages>
-__global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUtensorMap map, const SweepArgs a) {
+// grid = (column blocks, row segments); block = 32·kW threads.
+template <int kCols, int kRows, int kStages, int kW>
+__global__ void __launch_bounds__(32 * kW) sweep_kernel(const __grid_constant__ CUtensorMap map, const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
+    __shared__ unsigned s_prev;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cb = blockIdx.x, seg = blockIdx.y;
     const long long rows_per = ((a.n + a.nseg - 1) / a.nseg + kRows - 1) / kRows * kRows;
     const long long row_lo = (long long)seg * rows_per;
@@ -162,12 +176,12 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     // M is written only by sweeps of this handle, and the kernel before this one is never such a sweep still in flight
     // (a finish kernel triggers its successor only after its own pdl_wait, i.e. after the previous sweep completed).
     if (ntiles > 0) {
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             for (int s = 0; s < kStages; ++s) mbar_init(&ring.bars[s], 2);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             for (int t = 0; t < pre; ++t) ring.issue_m(&map, t, row_lo + (long long)t * kRows, (long long)cb * kCols);
         }
-        __syncwarp();
+        cta_sync<kW>();
     }
     if (a.exchange) pdl_trigger();   // the finish kernel's CTAs may become resident now (a flush sweep keeps its successor out)
     pdl_wait();                      // the preceding kernel (finish of the previous update, or whatever produced g) is complete
@@ -175,16 +189,16 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
     if (ntiles > 0) {
         const int pending = a.sc->pending;
         const double scale = a.sc->scale;
-        if (!pending) sweep_body<kCols, kRows, kStages, false, false>(&map, a, row_lo, row_hi, 1.0, ring, ntiles, pre, acc0, acc1);
-        else if (scale == 1.0) sweep_body<kCols, kRows, kStages, true, false>(&map, a, row_lo, row_hi, 1.0, ring, ntiles, pre, acc0, acc1);
-        else sweep_body<kCols, kRows, kStages, true, true>(&map, a, row_lo, row_hi, scale, ring, ntiles, pre, acc0, acc1);
+        if (!pending) sweep_body<kCols, kRows, kStages, kW, false, false>(&map, a, row_lo, row_hi, 1.0, ring, ntiles, pre, acc0, acc1);
+        else if (scale == 1.0) sweep_body<kCols, kRows, kStages, kW, true, false>(&map, a, row_lo, row_hi, 1.0, ring, ntiles, pre, acc0, acc1);
+        else sweep_body<kCols, kRows, kStages, kW, true, true>(&map, a, row_lo, row_hi, scale, ring, ntiles, pre, acc0, acc1);
     }
     if (!a.exchange) return;   // flush: only the deferred rank-1 was wanted
 
     // ---- tail: the last row segment of a column block sums the segments in order and publishes the block
-    constexpr int kPerLane = kCols == 64 ? 2 : 1;
+    constexpr int kPerLane = (kCols == 64 && kW == 1) ? 2 : 1;
     const bool lane_on = kCols >= 32 || lane < kCols;
-    const long long cl = (long long)cb * kCols + kPerLane * (lane_on ? lane : 0);   // local column of this lane
+    const long long cl = (long long)cb * kCols + (kW == 2 ? 32 * wid + lane : kPerLane * (lane_on ? lane : 0));   // local column of this lane
     if (a.nseg > 1) {
         double* out = a.partial + (long long)seg * a.ld_part;
         if (lane_on) {
@@ -192,11 +206,12 @@ __global__ void __launch_bounds__(32) sweep_kernel(const __grid_constant__ CUten
             if (kPerLane == 2) out[cl + 1] = acc1;
         }
         __threadfence();
-        unsigned prev = 0;
-        if (lane == 0) prev = atomicAdd(&a.cnt_block[cb], 1u);
-        prev = __shfl_sync(0xffffffffu, prev, 0);
+        cta_sync<kW>();
+        if (threadIdx.x == 0) s_prev = atomicAdd(&a.cnt_block[cb], 1u);
+        cta_sync<kW>();
+        const unsigned prev = s_prev;
         if (prev != (unsigned)(a.nseg - 1)) return;
-        if (lane == 0) a.cnt_block[cb] = 0;
+        if (threadIdx.x == 0) a.cnt_block[cb] = 0;
         __threadfence();
         acc0 = __ldcg(a.partial + cl);
         acc1 = kPerLane == 2 ? __ldcg(a.partial + cl + 1) : 0.0;
@@ -287,10 +302,30 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         }
         if (tid == 0) s_omega = acc;
     } else {
-        // blocked: thread t sums elements t, t+1024, … in order, then a fixed binary tree — deterministic, the same on every rank
+        // blocked: thread t sums elements t, t+1024, … in order, then a fixed binary tree — deterministic, the same on every rank.
+        // The lines are requested 8 at a time before any of them is checked: one L2 round trip per batch instead of one per line.
         double acc = 0.0;
+        long long k = tid;
+        if (ll && !dead) {
+            for (; k + 7 * kFinThreads < n; k += 8 * kFinThreads) {
+                unsigned w[8][4];
+                double gk[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint4* line = lines + k + (long long)u * kFinThreads;
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]) : "l"(line) : "memory");
+                    gk[u] = g[k + (long long)u * kFinThreads];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    double v = __hiloint2double((int)w[u][2], (int)w[u][0]);
+                    if (w[u][1] != flag || w[u][3] != flag) v = load_gt(k + (long long)u * kFinThreads);   // not there yet: poll
+                    acc += gk[u] * v;
+                }
+            }
+        }
 #pragma unroll 4
-        for (long long k = tid; k < n; k += kFinThreads) acc += g[k] * load_gt(k);
+        for (; k < n; k += kFinThreads) acc += g[k] * load_gt(k);
         prod[tid] = acc;
         __syncthreads();
         for (int off = kFinThreads / 2; off > 0; off >>= 1) {
@@ -493,7 +528,7 @@ int alloc_ctx(ellcuda_ctx* h) {
     return make_tensor_map(&h->map, h->S, n, h->w, h->ld, h->tile_rows, h->cols);
 }
 
-template <int CO, int R, int ST>
+template <int CO, int R, int ST, int W>
 int launch_sweep_t(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {
     // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: one bit per device ordinal,
     // per instantiation, set under a mutex (handles on several devices / host threads in one process)
@@ -504,30 +539,33 @@ int launch_sweep_t(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s
         std::lock_guard<std::mutex> lk(mu);
         const bool known = h->device < 64 && ((done_mask >> h->device) & 1ULL);
         if (!known) {
-            ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<CO, R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ELL_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<CO, R, ST, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (h->device < 64) done_mask |= 1ULL << h->device;
         }
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = grid; cfg.blockDim = dim3(32 * W); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: the prologue (barriers, first tiles of M) may
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // overlap the finish kernel of the previous update
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sweep_kernel<CO, R, ST>, h->asym_live ? h->mapA : h->map, a));
+    ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sweep_kernel<CO, R, ST, W>, h->asym_live ? h->mapA : h->map, a));
     return ELLCUDA_OK;
 }
 
 int launch_sweep(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) {
-    if (h->cols == 32) return launch_sweep_t<32, 64, 4>(h, grid, a, s);
-    if (h->cols == 16) return launch_sweep_t<16, 64, 6>(h, grid, a, s);
+    if (h->cols == 32) return launch_sweep_t<32, 64, 4, 1>(h, grid, a, s);
+    if (h->cols == 16) return launch_sweep_t<16, 64, 6, 1>(h, grid, a, s);
     const int key = h->tile_rows * 100 + h->stages;   // 64-column blocks: tile rows x ring depth (ELLCUDA_SWEEP, experiments)
     switch (key) {
-        case 1608: return launch_sweep_t<64, 16, 8>(h, grid, a, s);
-        case 3204: return launch_sweep_t<64, 32, 4>(h, grid, a, s);
-        case 3206: return launch_sweep_t<64, 32, 6>(h, grid, a, s);
-        case 4804: return launch_sweep_t<64, 48, 4>(h, grid, a, s);
-        default: return launch_sweep_t<64, 64, 3>(h, grid, a, s);
+        case 1608: return launch_sweep_t<64, 16, 8, 1>(h, grid, a, s);
+        case 3204: return launch_sweep_t<64, 32, 4, 1>(h, grid, a, s);
+        case 3206: return launch_sweep_t<64, 32, 6, 1>(h, grid, a, s);
+        case 4804: return launch_sweep_t<64, 48, 4, 1>(h, grid, a, s);
+        default:
+            // two warps per CTA (one column per lane) unless ELLCUDA_SWEEP_WARPS=1 asks for the single-warp form
+            if (ELL_ENV_INT("ELLCUDA_SWEEP_WARPS", 2) == 1) return launch_sweep_t<64, 64, 3, 1>(h, grid, a, s);
+            return launch_sweep_t<64, 64, 3, 2>(h, grid, a, s);
     }
 }
 
