@@ -89,11 +89,19 @@ __device__ int stable_update(const CalcConsts& cc, int which, const WarpMem& wm,
     const double mu = r.sigma / (1.0 - r.sigma);
     double oldt = omega / mu;
     double oldt0 = 0.0, t0 = 1.0, oldt1 = 0.0, t1 = 1.0;
-    for (int j = 0; j < n; ++j) {            // temp = oldt + gg[j]; oldt = temp   — one ordered chain, every lane
-        const double temp = oldt + wm.sv[j];
-        if (j == i0) { oldt0 = oldt; t0 = temp; }
-        if (j == i1) { oldt1 = oldt; t1 = temp; }
-        oldt = temp;
+    {   // temp = oldt + gg[j]; oldt = temp — one ordered chain, run by every lane, the running values parked in sz so that each
+        // lane picks its two afterwards (selecting inside the loop cost 5 instructions per step instead of 1)
+        const double oldt_init = oldt;
+        __syncwarp();
+        for (int j = 0; j < n; ++j) {
+            const double temp = oldt + wm.sv[j];
+            if (lane == 0) wm.sz[j] = temp;
+            oldt = temp;
+        }
+        __syncwarp();
+        if (on0) { oldt0 = i0 == 0 ? oldt_init : wm.sz[i0 - 1]; t0 = wm.sz[i0]; }
+        if (on1) { oldt1 = wm.sz[i1 - 1]; t1 = wm.sz[i1]; }
+        __syncwarp();
     }
     const double nd0 = d0 * (oldt0 / t0), nd1 = d1 * (oldt1 / t1);   // mq[j][j] *= oldt / temp
     if (DIAG) {

@@ -42,6 +42,7 @@ struct SymArgs {
     long long npad;
     int T, nseg;
     int exchange;          // 0: flush only (apply the deferred rank-1, produce nothing)
+    int use_map;           // 1: tiles move by cp.async.bulk.tensor.2d over the packed buffer seen as a (tiles·64) x 64 matrix
 };
 
 __device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, unsigned bytes) {
@@ -59,10 +60,11 @@ struct SymRing {
         gcol = reinterpret_cast<double*>(gss + kSymStages * kVecBytes);
         bars = reinterpret_cast<unsigned long long*>(gss + kSymStages * kVecBytes + kVecBytes);
     }
-    __device__ __forceinline__ void issue_m(const SymArgs& a, int t, long long I, long long J) const {
+    __device__ __forceinline__ void issue_m(const SymArgs& a, const CUtensorMap* map, int t, long long I, long long J) const {
         const int s = t % kSymStages;
         mbar_expect_tx(&bars[s], kTileBytes);
-        bulk_load_1d(tiles + s * kTileBytes, a.Mp + tile_index(I, J) * kTileDoubles, kTileBytes, &bars[s]);
+        if (a.use_map) tma_load_2d(tiles + s * kTileBytes, map, 0, (int)(tile_index(I, J) * kTile), &bars[s]);
+        else bulk_load_1d(tiles + s * kTileBytes, a.Mp + tile_index(I, J) * kTileDoubles, kTileBytes, &bars[s]);
     }
     template <bool PENDING>
     __device__ __forceinline__ void issue_v(const SymArgs& a, int t, long long I) const {
@@ -87,7 +89,7 @@ struct Chunk {   // this warp's part of its pair's tile list
 // 32w..32w+31 (one per lane).  With a single warp the tile cost 1730 dependent instructions at ~3.5 clocks each = 3 us against
 // 2.7 us of HBM time per tile (ncu: 28 % issue active, 71 % of the copy bandwidth); split over two warps it is well below.
 template <bool PENDING, bool SCALE>
-__device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, const Chunk& ch, int pre, double scale) {
+__device__ __forceinline__ void sym_body(const SymArgs& a, const CUtensorMap* map, const SymRing& ring, const Chunk& ch, int pre, double scale) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lcol = 32 * wid + lane;   // this thread's column in pass 1, row in pass 2
     const int seg = blockIdx.y;
@@ -145,7 +147,8 @@ __device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, 
         __syncthreads();
         if (threadIdx.x == 0) {
             if (PENDING) {
-                bulk_store_1d(a.Mp + tile_index(I, J) * kTileDoubles, tile, kTileBytes);
+                if (a.use_map) tma_store_2d(map, 0, (int)(tile_index(I, J) * kTile), tile);
+                else bulk_store_1d(a.Mp + tile_index(I, J) * kTileDoubles, tile, kTileBytes);
                 bulk_commit();
             }
             const int nt = t + kSymStages - 1;  // refill the stage whose store was issued one iteration ago
@@ -153,7 +156,7 @@ __device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, 
                 if (PENDING) bulk_wait_read<1>();
                 int In, Jn;
                 ch.tile_of(nt, In, Jn);
-                ring.issue_m(a, nt, In, Jn);
+                ring.issue_m(a, map, nt, In, Jn);
                 ring.issue_v<PENDING>(a, nt, In);
             }
         }
@@ -163,7 +166,7 @@ __device__ __forceinline__ void sym_body(const SymArgs& a, const SymRing& ring, 
 }
 
 // grid = (pairs of column blocks, row segments); block = 64 threads
-__global__ void __launch_bounds__(64) sym_sweep_kernel(const SymArgs a) {
+__global__ void __launch_bounds__(64) sym_sweep_kernel(const __grid_constant__ CUtensorMap map, const SymArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SymRing ring(smem_raw);
     Chunk ch;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(64) sym_sweep_kernel(const SymArgs a) {
         for (int t = 0; t < pre; ++t) {
             int I, J;
             ch.tile_of(t, I, J);
-            ring.issue_m(a, t, I, J);
+            ring.issue_m(a, &map, t, I, J);
         }
     }
     __syncthreads();
@@ -192,9 +195,9 @@ __global__ void __launch_bounds__(64) sym_sweep_kernel(const SymArgs a) {
     pdl_wait();
     const int pending = a.sc->pending;
     const double scale = a.sc->scale;
-    if (!pending) sym_body<false, false>(a, ring, ch, pre, 1.0);
-    else if (scale == 1.0) sym_body<true, false>(a, ring, ch, pre, 1.0);
-    else sym_body<true, true>(a, ring, ch, pre, scale);
+    if (!pending) sym_body<false, false>(a, &map, ring, ch, pre, 1.0);
+    else if (scale == 1.0) sym_body<true, false>(a, &map, ring, ch, pre, 1.0);
+    else sym_body<true, true>(a, &map, ring, ch, pre, scale);
 }
 
 // grad_t[i] = (column sums of block B = i/64, segment slots in order) + (row sums rowpart[J][i], J = 0..B-1 in order)
@@ -244,7 +247,8 @@ int sym_alloc(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMalloc(&h->rowpart, (size_t)h->T * npad * 8));
     ELL_CUDA_TRY(cudaMemset(h->colpart, 0, (size_t)nseg * npad * 8));
     ELL_CUDA_TRY(cudaMemset(h->rowpart, 0, (size_t)h->T * npad * 8));
-    return ELLCUDA_OK;
+    // the packed tiles as a tall matrix of 64 columns: tile k = rows [64k, 64k+64), so a tile is one 64x64 TMA box
+    return make_tensor_map(&h->map, h->Mp, (long long)tiles * kTile, kTile, kTile, kTile, kTile);
 }
 
 void sym_free(ellcuda_ctx* h) {
@@ -300,13 +304,14 @@ int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_o
     SymArgs a;
     a.Mp = h->Mp; a.g = g_dev; a.pend = h->pend; a.sc = h->sc; a.colpart = h->colpart; a.rowpart = h->rowpart;
     a.npad = h->T * kTile; a.T = (int)h->T; a.nseg = h->sym_nseg; a.exchange = exchange;
+    a.use_map = ELL_ENV_INT("ELLCUDA_SYM_TMA", 1);   // 0: plain 1-D bulk copies of the contiguous 32 KB tile (experiments)
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)((h->T + 1) / 2), (unsigned)h->sym_nseg); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = kSymSmem; cfg.stream = s;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sym_sweep_kernel, a));
+    ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sym_sweep_kernel, h->map, a));
     h->launches += 1;
     if (!exchange) return ELLCUDA_OK;
     cudaLaunchConfig_t cc{};

@@ -88,11 +88,10 @@ struct Ring {
     }
 };
 
-// kW = warps per CTA.  One warp (two columns per lane) is what the narrow column blocks and small matrices use; with two warps
-// each lane owns ONE column (warp w: columns 32w..32w+31 of the block), which halves the dependent instruction stream per
-// tile: ncu showed the single warp issuing 18 % of the time with the rest spent on its own dependencies, i.e. 2.2 us of
-// instruction latency per 32 KB tile against 2.56 us of HBM time — two warps put the tile's work well under its HBM time.
-// The sums are still per column, rows ascending: bit-identical.
+// kW = warps per CTA.  One warp (two columns per lane) is the default.  ncu shows that warp issuing 18 % of the time with the
+// rest spent on its own dependencies (2.2 us of instruction latency per 32 KB tile against 2.56 us of HBM time), so a
+// two-warp form was built (warp w: columns 32w..32w+31, one per lane; still per column, rows ascending: bit-identical) —
+// it measured no faster (see launch_sweep), the per-tile CTA barrier costs what the shorter instruction stream saves.
 template <int kW>
 __device__ __forceinline__ void cta_sync() {
     if (kW == 1) __syncwarp();
@@ -422,39 +421,6 @@ __global__ void fill_diag_kernel(double* __restrict__ s, long long ld, long long
     if (i < n) s[i * ld + c] = diag ? diag[i] : 1.0;
 }
 
-// ------------------------------------------------------------------------------------------------ tensor map
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_tensor_map(CUtensorMap* map, void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols) {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        ELL_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return ELLCUDA_E_CUDA; }
-        fn = (EncodeTiledFn)p;
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    if (const char* e = getenv("ELLCUDA_L2PROMO")) {   // performance experiments
-        const int v = atoi(e);
-        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-              : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    }
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-        return ELLCUDA_E_CUDA;
-    }
-    return ELLCUDA_OK;
-}
-
 constexpr size_t sweep_smem(int cols, int rows, int stages) { return (size_t)stages * (cols * rows * 8 + rows * 24) + stages * 8 + 128; }
 
 }  // namespace
@@ -563,9 +529,10 @@ int launch_sweep(ellcuda_ctx* h, dim3 grid, const SweepArgs& a, cudaStream_t s) 
         case 3206: return launch_sweep_t<64, 32, 6, 1>(h, grid, a, s);
         case 4804: return launch_sweep_t<64, 48, 4, 1>(h, grid, a, s);
         default:
-            // two warps per CTA (one column per lane) unless ELLCUDA_SWEEP_WARPS=1 asks for the single-warp form
-            if (ELL_ENV_INT("ELLCUDA_SWEEP_WARPS", 2) == 1) return launch_sweep_t<64, 64, 3, 1>(h, grid, a, s);
-            return launch_sweep_t<64, 64, 3, 2>(h, grid, a, s);
+            // one warp per CTA with two columns per lane; ELLCUDA_SWEEP_WARPS=2 selects two warps with one column per lane
+            // (measured at n=16384: 711 us per sweep against 680 on the whole matrix, 100.4 against 99.5 us on a 1/8 slab)
+            if (ELL_ENV_INT("ELLCUDA_SWEEP_WARPS", 1) == 2) return launch_sweep_t<64, 64, 3, 2>(h, grid, a, s);
+            return launch_sweep_t<64, 64, 3, 1>(h, grid, a, s);
     }
 }
 
