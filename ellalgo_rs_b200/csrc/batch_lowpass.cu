@@ -317,16 +317,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
             xc -= rho_over_omega * gt;
             const double ratio = r.sigma / omega;
             const double rg = ratio * gt;
-            c.srg()[lane] = rg;
-            __syncwarp();
-            // element (lane, j): hi = max(lane, j) supplies ratio*grad_t, lo = min(lane, j) supplies grad_t
+            // element (lane, j): hi = max(lane, j) supplies ratio*grad_t, lo = min(lane, j) supplies grad_t.  ratio*grad_t[j] is
+            // recomputed from the broadcast grad_t[j] (same operands, same rounding as in lane j) instead of being exchanged through
+            // shared memory: 34 fewer wavefronts per iteration on the unit that bounds this kernel, for 32 more DMULs.
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 const double2 gv = *reinterpret_cast<const double2*>(c.sgt() + j);
-                const double2 rv = *reinterpret_cast<const double2*>(c.srg() + j);
                 double u0, u1;
-                if (j <= lane) u0 = rg * gv.x; else u0 = rv.x * gt;
-                if (j + 1 <= lane) u1 = rg * gv.y; else u1 = rv.y * gt;
+                if (j <= lane) u0 = rg * gv.x; else u0 = (ratio * gv.x) * gt;
+                if (j + 1 <= lane) u1 = rg * gv.y; else u1 = (ratio * gv.y) * gt;
                 m[j] -= u0;
                 m[j + 1] -= u1;
             }
