@@ -32,7 +32,13 @@ __device__ __forceinline__ double seq_sum_pair(double* s, double lo, double hi, 
     if (lane + 32 < kNMax) s[lane + 32] = hi;
     __syncwarp();
     double acc = 0.0;
-    for (int k = 0; k < n; ++k) acc += s[k];
+    int k = 0;
+    for (; k + 1 < n; k += 2) {   // two per load, still one ordered chain
+        const double2 v = *reinterpret_cast<const double2*>(s + k);
+        acc += v.x;
+        acc += v.y;
+    }
+    if (k < n) acc += s[k];
     __syncwarp();
     return acc;
 }
@@ -217,8 +223,8 @@ __global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, i
 __global__ void __launch_bounds__(32) stable_single_kernel(double* __restrict__ qu_g, double* __restrict__ xc_g, double* __restrict__ scal,
                                                            int* __restrict__ status_out, const double* __restrict__ g, int n,
                                                            CalcConsts cc, int which, Cut cut) {
-    __shared__ double s_qu[kNMax * (kNMax + 1) / 2];
-    __shared__ double s_vec[3 * kNMax];
+    __shared__ __align__(16) double s_qu[kNMax * (kNMax + 1) / 2];
+    __shared__ __align__(16) double s_vec[3 * kNMax];
     const int lane = threadIdx.x;
     const int tri = n * (n + 1) / 2;
     for (int e = lane; e < tri; e += 32) s_qu[e] = qu_g[e];

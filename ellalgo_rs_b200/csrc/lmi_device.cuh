@@ -175,17 +175,36 @@ __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, doub
     for (int i = 0; i < pos; ++i) {
         const double wi = wm.swit[i];
         int e = tri_index(i, 0);
-        for (int j = 0; j <= i; ++j, ++e) {          // F[i][j], j <= i: row i of the packed lower triangle
+        int j = 0;
+        for (; j + 1 <= i; j += 2, e += 2) {         // F[i][j], j <= i: row i of the packed lower triangle (two per trip)
+            const double wj0 = wm.swit[j], wj1 = wm.swit[j + 1];
+            const double a0 = f0[e], a1 = f1[e], b0 = f0[e + 1], b1 = f1[e + 1];
+            r0 += wi * a0 * wj0;
+            r1 += wi * a1 * wj0;
+            r0 += wi * b0 * wj1;
+            r1 += wi * b1 * wj1;
+        }
+        if (j <= i) {
             const double wj = wm.swit[j];
             r0 += wi * f0[e] * wj;
             r1 += wi * f1[e] * wj;
         }
         e = tri_index(i + 1, i);
-        for (int j = i + 1; j < pos; ++j) {           // F[i][j] = F[j][i], j > i: walk down column i
+        j = i + 1;
+        for (; j + 1 < pos; j += 2) {                 // F[i][j] = F[j][i], j > i: walk down column i (two per trip)
+            const int e2 = e + j + 1;
+            const double wj0 = wm.swit[j], wj1 = wm.swit[j + 1];
+            const double a0 = f0[e], a1 = f1[e], b0 = f0[e2], b1 = f1[e2];
+            r0 += wi * a0 * wj0;
+            r1 += wi * a1 * wj0;
+            r0 += wi * b0 * wj1;
+            r1 += wi * b1 * wj1;
+            e = e2 + j + 2;
+        }
+        if (j < pos) {
             const double wj = wm.swit[j];
             r0 += wi * f0[e] * wj;
             r1 += wi * f1[e] * wj;
-            e += j + 1;
         }
     }
     if (L.lmi0) { r0 = -r0; r1 = -r1; }   // g[k] = -sym_quad(F_k), lmi0_oracle.rs:31
