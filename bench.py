@@ -546,13 +546,17 @@ def main():
             its = sum_over_ranks(float(iterations_done(ni, es)))
             # e2e: host buffers through ellcuda_batch_solve (H2D + kernel + D2H inside the call)
             host.device = local
-            t0 = time.perf_counter()
-            ho = batch.solve_batch(host, stream=sptr)
-            t_e2e = max_over_ranks(time.perf_counter() - t0)
+            t_e2e = None
+            for _ in range(2):          # the first call also pays the allocations of its staging buffers
+                t0 = time.perf_counter()
+                ho = batch.solve_batch(host, stream=sptr)
+                dt = time.perf_counter() - t0
+                t_e2e = dt if t_e2e is None else min(t_e2e, dt)
+            t_e2e = max_over_ranks(t_e2e)
             its_e2e = sum_over_ranks(float(iterations_done(ho.num_iters, ho.exit_status)))
             return {"value": its / best, "unit": "iterations/s", "ms": 1e3 * best, "problems_per_gpu": host.count,
                     "problems_per_s": host.count * world / best, "iterations_per_gpu": iterations_done(ni, es),
-                    "e2e": {"value": its_e2e / t_e2e, "unit": "iterations/s", "timing": "host wall clock around ellcuda_batch_solve with host buffers"}}, ni, es
+                    "e2e": {"value": its_e2e / t_e2e, "unit": "iterations/s", "timing": "host wall clock around ellcuda_batch_solve with host buffers (pageable), best of 2"}}, ni, es
 
         cpu_ok = rank == 0 and world == 1 and not args.skip_cpu
         c1 = 1 << 20
