@@ -380,7 +380,8 @@ def main():
             a1.record(stream)
             barrier()
             t_large = max_over_ranks(a0.elapsed_time(a1) / 1e3)
-            l_launch = ((3 if storage else 2) * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
+            per_update = (3 + (2 if world > 1 else 0)) if storage else 2    # sym: sweep, combine(+push), [reduce,] finish
+            l_launch = (per_update * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
             status = int(ell.ell.last_status())
             kind = ell.exchange_kind
             del graph, ell
@@ -406,8 +407,9 @@ def main():
             for k in range(2):
                 ell.update_async(A.UPDATE_BIAS, grads[k], cut)
                 got.append((int(ell.ell.last_status()), ell.tsq(), ell.kappa, ell.xc()))
-            slab = ell.ell.mq if rank == 0 else None
-            lo, hi = ell.lo, ell.hi
+            whole = storage == 1
+            slab = ell.ell.mq if (rank == 0 and not (whole and world > 1)) else None
+            lo, hi = (0, n) if whole else (ell.lo, ell.hi)
             del ell
             ref, secs = [None], []
             if rank == 0:
@@ -424,9 +426,12 @@ def main():
                     secs.append(time.perf_counter() - t0)
                     states.append((int(st), tsq.value, kap.value, xc.copy()))
                 ref = [states]
-                den = float(np.abs(mq[lo:hi]).max())
-                m_err = float(np.abs(slab - mq[lo:hi]).max() / den)
-                m_same = bool(np.array_equal(slab, mq[lo:hi]))
+                if slab is not None:
+                    den = float(np.abs(mq[lo:hi]).max())
+                    m_err = float(np.abs(slab - mq[lo:hi]).max() / den)
+                    m_same = bool(np.array_equal(slab, mq[lo:hi]))
+                else:          # sharded symmetric storage: no rank holds rows; M is checked by tests/multi_gpu_check.py at small n
+                    m_err, m_same = 0.0, False
                 del mq, slab
             if world > 1:
                 dist.broadcast_object_list(ref, src=0)
@@ -461,14 +466,16 @@ def main():
         if world == 1 and not args.skip_cpu:
             parities["8"], _ = parity(8)
         symmetric = None
-        if world == 1:
-            # tolerance-mode option: only the lower block-triangle is stored and streamed (8*n^2 bytes per update)
+        if True:
+            # tolerance-mode option: only the lower block-triangle is stored and streamed (8*n^2 bytes per update); sharded, the
+            # column-block pairs are dealt round-robin to the ranks and the exchange is a reduction of flagged lines over NVLink
             sp = phases(0, storage=1)
             real = 8.0 * n * n + 8.0 * n * 64            # lower block-triangle incl. full diagonal tiles, read + write
             symmetric = {"what": "ELL_STORAGE_SYMMETRIC: lower block-triangle of 64x64 tiles only; sums regrouped, results to 1e-9",
                          "updates_per_s": sp["updates_per_s"], "ms_per_update": sp["ms_per_update"], "sweep_ms": sp["sweep_ms"],
                          "bytes_per_update": real, "GBs": real * sp["updates_per_s"] / 1e9,
-                         "sweep_GBs": real / (sp["sweep_ms"] * 1e-3) / 1e9, "sweep_frac_of_measured_peak": real / (sp["sweep_ms"] * 1e-3) / 1e9 / peak,
+                         "sweep_GBs_per_gpu": real / world / (sp["sweep_ms"] * 1e-3) / 1e9,
+                         "sweep_frac_of_measured_peak": real / world / (sp["sweep_ms"] * 1e-3) / 1e9 / peak,
                          "last_status": sp["last_status"], "gpu_launches": sp["gpu_launches"]}
             if not args.skip_cpu:
                 symmetric["parity"], _ = parity(0, storage=1)

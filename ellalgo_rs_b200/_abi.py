@@ -62,4 +62,5 @@ class CreateDesc(C.Structure):
         ("row_begin", C.c_int64), ("row_end", C.c_int64),
         ("reduce_mode", C.c_int32), ("storage", C.c_int32),
         ("stream", C.c_void_p),
+        ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
     ]

@@ -97,6 +97,11 @@ struct PeerTable {
 // lines[2][n] of 16 bytes (peer exchange, buffer = epoch parity)
 __host__ __device__ inline size_t xblk_plain_doubles(long long n) { return (size_t)((n + 1) & ~1LL); }
 __host__ __device__ inline size_t xblk_doubles(long long n) { return xblk_plain_doubles(n) + (size_t)4 * n; }
+// sharded symmetric storage adds, after the lines: parts[2][nranks][slice] lines — rank r's partial sums for the elements this
+// rank reduces (buffer = epoch parity)
+__host__ __device__ inline uint4* xblk_parts(double* blk, long long n, int parity, int nranks, int src, long long slice) {
+    return reinterpret_cast<uint4*>(blk + xblk_doubles(n)) + ((long long)parity * nranks + src) * slice;
+}
 __host__ __device__ inline uint4* xblk_lines(double* blk, long long n, int parity) {
     return reinterpret_cast<uint4*>(blk + xblk_plain_doubles(n)) + (long long)parity * n;
 }
@@ -258,6 +263,8 @@ struct ellcuda_ctx {
     double* rowpart = nullptr;  // T x npad64: rowpart[J][i] = sum over the columns of block J of M[i][c] g[c], for rows below block J
     long long T = 0;            // tile rows
     int sym_nseg = 1;
+    int sym_rank = 0, sym_count = 1;   // sharded symmetric storage: this handle keeps the pairs p = sym_rank (mod sym_count) current
+    long long sym_slice = 0;    // ceil(n / sym_count): the elements of grad_t this rank reduces
     std::vector<ellcuda_ctx*> parts;
     double* ytmp = nullptr;     // group members: slab of a dot_mv result before it is copied to the caller's vector
     int which = 0;
@@ -275,6 +282,7 @@ int sym_alloc(ellcuda_ctx* h);
 void sym_free(ellcuda_ctx* h);
 int sym_upload(ellcuda_ctx* h, const double* mq_host, const double* diag_host);          // synchronous
 int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_out);     // sweep (+ combine into grad_t / plain_out)
+int sym_reduce(ellcuda_ctx* h);    // sharded: sum the ranks' partials of this rank's slice, broadcast the result (after sym_sweep on every rank)
 int sym_unpack(ellcuda_ctx* h, double* out_dev_n_by_n);                                  // the full matrix, row-major, device
 int sym_copy(ellcuda_ctx* dst, const ellcuda_ctx* src, cudaStream_t s);
 }  // namespace ellcuda

@@ -43,6 +43,7 @@ struct SymArgs {
     int T, nseg;
     int exchange;          // 0: flush only (apply the deferred rank-1, produce nothing)
     int use_map;           // 1: tiles move by cp.async.bulk.tensor.2d over the packed buffer seen as a (tiles·64) x 64 matrix
+    int rank, count;       // sharded: this launch covers the pairs rank, rank + count, ... (whole: 0, 1)
 };
 
 __device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, unsigned bytes) {
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(64) sym_sweep_kernel(const __grid_constant__ C
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SymRing ring(smem_raw);
     Chunk ch;
-    ch.Ja = blockIdx.x;
-    ch.Jb = a.T - 1 - blockIdx.x;
+    ch.Ja = a.rank + blockIdx.x * a.count;
+    ch.Jb = a.T - 1 - ch.Ja;
     ch.lenA = a.T - ch.Ja;
     const int lenB = ch.Jb != ch.Ja ? a.T - ch.Jb : 0;
     const int total = ch.lenA + lenB;
@@ -223,6 +224,48 @@ __global__ void __launch_bounds__(256) sym_combine_kernel(const double* __restri
     out[i] = s;
 }
 
+// Sharded symmetric storage: every rank has partial sums for ALL n elements (from its tiles), so the exchange is a reduction.
+// Phase 1 (this kernel): element i's local partial goes, as a flagged line, to the rank that reduces i (slices of `slice`).
+__global__ void __launch_bounds__(256) sym_combine_push_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
+                                                               long long n, long long npad, int nseg, PeerTable pt, const Scal* sc,
+                                                               long long slice) {
+    pdl_trigger();
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || sc->failed) return;
+    const int B = (int)(i >> 6);
+    double s = 0.0;
+    for (int k = 0; k < nseg; ++k) s += __ldcg(colpart + (long long)k * npad + i);
+#pragma unroll 4
+    for (int J = 0; J < B; ++J) s += __ldcg(rowpart + (long long)J * npad + i);
+    const unsigned long long epoch = sc->epoch;
+    const int o = (int)(i / slice);
+    ll_store(xblk_parts(pt.blk[o], n, (int)(epoch & 1ULL), pt.nranks, pt.rank, slice) + (i - (long long)o * slice), s, (unsigned)epoch);
+}
+
+// Phase 2: this rank's slice — the P partials in rank order (identical on every rank by construction: one rank does it),
+// then the sum as a flagged line into every rank's grad_t lines, which finish_kernel polls as for a gathered exchange.
+__global__ void __launch_bounds__(256) sym_reduce_kernel(long long n, PeerTable pt, Scal* sc, long long slice) {
+    pdl_trigger();
+    pdl_wait();
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (long long)pt.rank * slice + j;
+    if (j >= slice || i >= n || sc->failed) return;
+    const unsigned long long epoch = sc->epoch;
+    const int par = (int)(epoch & 1ULL);
+    const unsigned flag = (unsigned)epoch;
+    double t = 0.0;
+    for (int r = 0; r < pt.nranks; ++r) {
+        double v = 0.0;
+        if (!ll_load(xblk_parts(pt.blk[pt.rank], n, par, pt.nranks, r, slice) + j, flag, v)) {
+            atomicExch(&sc->failed, 1);   // a peer never delivered: the handle is dead (finish reports Unknown from now on)
+            return;
+        }
+        t += v;
+    }
+    for (int r = 0; r < pt.nranks; ++r) ll_store(xblk_lines(pt.blk[r], n, par) + i, t, flag);
+}
+
 __global__ void sym_fill_diag_kernel(double* __restrict__ Mp, long long n, const double* __restrict__ diag) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -244,8 +287,11 @@ __global__ void sym_unpack_kernel(const double* __restrict__ Mp, double* __restr
 int sym_alloc(ellcuda_ctx* h) {
     h->T = (h->n + kTile - 1) / kTile;
     const long long npad = h->T * kTile;
-    const long long npairs = (h->T + 1) / 2;
-    int nseg = h->reduce_mode > 0 ? h->reduce_mode : (int)((256 + npairs - 1) / npairs);   // ~256 streaming warps
+    const long long all_pairs = (h->T + 1) / 2;
+    long long npairs = (all_pairs - h->sym_rank + h->sym_count - 1) / h->sym_count;          // the pairs this handle owns
+    if (npairs < 1) npairs = 1;
+    h->sym_slice = (h->n + h->sym_count - 1) / h->sym_count;
+    int nseg = h->reduce_mode > 0 ? h->reduce_mode : (int)((256 + npairs - 1) / npairs);   // ~256 streaming CTAs
     if (nseg < 1) nseg = 1;
     if (nseg > 16) nseg = 16;
     h->sym_nseg = nseg;
@@ -313,20 +359,55 @@ int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_o
     a.Mp = h->Mp; a.g = g_dev; a.pend = h->pend; a.sc = h->sc; a.colpart = h->colpart; a.rowpart = h->rowpart;
     a.npad = h->T * kTile; a.T = (int)h->T; a.nseg = h->sym_nseg; a.exchange = exchange;
     a.use_map = ELL_ENV_INT("ELLCUDA_SYM_TMA", 1);   // 0: plain 1-D bulk copies of the contiguous 32 KB tile (experiments)
+    a.rank = h->sym_rank; a.count = h->sym_count;
+    const long long all_pairs = (h->T + 1) / 2;
+    const long long own_pairs = all_pairs > h->sym_rank ? (all_pairs - h->sym_rank + h->sym_count - 1) / h->sym_count : 0;
+    if (own_pairs == 0 && !exchange) return ELLCUDA_OK;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((h->T + 1) / 2), (unsigned)h->sym_nseg); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = kSymSmem; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)(own_pairs > 0 ? own_pairs : 1), (unsigned)h->sym_nseg); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = kSymSmem; cfg.stream = s;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sym_sweep_kernel, h->map, a));
-    h->launches += 1;
+    if (own_pairs > 0) {
+        ELL_CUDA_TRY(cudaLaunchKernelEx(&cfg, sym_sweep_kernel, h->map, a));
+        h->launches += 1;
+    }
     if (!exchange) return ELLCUDA_OK;
+    if (h->sym_count > 1 && !plain_out) {   // sharded: the local partial of every element goes to the rank that reduces it
+        if (h->nranks != h->sym_count) { set_error("a sharded symmetric handle must be attached to its peers before it is updated"); return ELLCUDA_E_ARG; }
+        PeerTable pt;
+        pt.nranks = h->nranks; pt.rank = h->rank;
+        for (int r = 0; r < kMaxRanks; ++r) pt.blk[r] = r < h->nranks ? h->peer_blk[r] : nullptr;
+        cudaLaunchConfig_t cc{};
+        cc.gridDim = dim3((unsigned)((h->n + 255) / 256)); cc.blockDim = dim3(256); cc.dynamicSmemBytes = 0; cc.stream = s;
+        cc.attrs = attr; cc.numAttrs = pdl_enabled() ? 1 : 0;
+        ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_combine_push_kernel, (const double*)h->colpart, (const double*)h->rowpart, h->n, a.npad,
+                                        a.nseg, pt, (const Scal*)h->sc, h->sym_slice));
+        h->launches += 1;
+        return ELLCUDA_OK;
+    }
     cudaLaunchConfig_t cc{};
     cc.gridDim = dim3((unsigned)((h->n + 255) / 256)); cc.blockDim = dim3(256); cc.dynamicSmemBytes = 0; cc.stream = s;
     cc.attrs = attr; cc.numAttrs = pdl_enabled() ? 1 : 0;
     ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_combine_kernel, (const double*)h->colpart, (const double*)h->rowpart,
                                     plain_out ? plain_out : h->xblk, h->n, a.npad, a.nseg));
+    h->launches += 1;
+    return ELLCUDA_OK;
+}
+
+int sym_reduce(ellcuda_ctx* h) {
+    if (h->sym_count <= 1) return ELLCUDA_OK;
+    PeerTable pt;
+    pt.nranks = h->nranks; pt.rank = h->rank;
+    for (int r = 0; r < kMaxRanks; ++r) pt.blk[r] = r < h->nranks ? h->peer_blk[r] : nullptr;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cc{};
+    cc.gridDim = dim3((unsigned)((h->sym_slice + 255) / 256)); cc.blockDim = dim3(256); cc.dynamicSmemBytes = 0; cc.stream = h->stream;
+    cc.attrs = attr; cc.numAttrs = pdl_enabled() ? 1 : 0;
+    ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_reduce_kernel, h->n, pt, h->sc, h->sym_slice));
     h->launches += 1;
     return ELLCUDA_OK;
 }

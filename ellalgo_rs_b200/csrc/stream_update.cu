@@ -476,7 +476,8 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMalloc(&h->gzero, (size_t)h->npad * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->gstage, (size_t)h->npad * 8));
     ELL_CUDA_TRY(cudaMallocHost(&h->status_host, sizeof(int)));
-    ELL_CUDA_TRY(cudaMalloc(&h->xblk, xblk_doubles(n) * 8));
+    const size_t xblk_total = xblk_doubles(n) + (h->sym && h->sym_count > 1 ? (size_t)4 * h->sym_count * ((n + h->sym_count - 1) / h->sym_count) : 0);
+    ELL_CUDA_TRY(cudaMalloc(&h->xblk, xblk_total * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->pend, pend_n * 16));
     ELL_CUDA_TRY(cudaMalloc(&h->partial, (size_t)h->nseg * h->ld_part * 8));
     ELL_CUDA_TRY(cudaMalloc(&h->counters, (size_t)(h->ncb + 2) * 4));
@@ -486,7 +487,7 @@ int alloc_ctx(ellcuda_ctx* h) {
     ELL_CUDA_TRY(cudaMemset(h->gpad, 0, (size_t)h->npad * 8));
     ELL_CUDA_TRY(cudaMemset(h->gzero, 0, (size_t)h->npad * 8));
     ELL_CUDA_TRY(cudaMemset(h->gstage, 0, (size_t)h->npad * 8));
-    ELL_CUDA_TRY(cudaMemset(h->xblk, 0, xblk_doubles(n) * 8));
+    ELL_CUDA_TRY(cudaMemset(h->xblk, 0, xblk_total * 8));
     ELL_CUDA_TRY(cudaMemset(h->pend, 0, pend_n * 16));
     ELL_CUDA_TRY(cudaMemset(h->counters, 0, (size_t)(h->ncb + 2) * 4));
     keep_mempool(h->device);
@@ -657,7 +658,12 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     if (d->reduce_mode < 0 || d->reduce_mode > 64) { set_error("reduce_mode must be in [0, 64]"); return ELLCUDA_E_ARG; }
     if (d->storage != ELL_STORAGE_FULL && d->storage != ELL_STORAGE_SYMMETRIC) { set_error("bad storage"); return ELLCUDA_E_ARG; }
     const bool sym = d->storage == ELL_STORAGE_SYMMETRIC;
-    if (sym && (rb != 0 || re != d->n)) { set_error("symmetric storage does not shard rows"); return ELLCUDA_E_ARG; }
+    if (sym && (rb != 0 || re != d->n)) { set_error("symmetric storage shards by shard_rank / shard_count, not by rows"); return ELLCUDA_E_ARG; }
+    const int shard_count = d->shard_count > 1 ? d->shard_count : 1;
+    if (shard_count > 1 && (!sym || shard_count > kMaxRanks || d->shard_rank < 0 || d->shard_rank >= shard_count)) {
+        set_error("shard_rank / shard_count apply to ELL_STORAGE_SYMMETRIC, 0 <= rank < count <= 16");
+        return ELLCUDA_E_ARG;
+    }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
         cudaGetLastError();
@@ -683,6 +689,8 @@ int ellcuda_create(const ell_create_desc* d, ell_handle* out) {
     ellcuda_ctx* h = new ellcuda_ctx();
     h->device = d->device;
     h->sym = sym;
+    h->sym_rank = shard_count > 1 ? d->shard_rank : 0;
+    h->sym_count = shard_count;
     h->n = d->n; h->c0 = rb; h->w = re - rb;
     h->reduce_mode = d->reduce_mode;
     h->nseg = d->reduce_mode > 0 ? d->reduce_mode : 1;
@@ -799,7 +807,7 @@ int ellcuda_clone(ell_handle h, ell_handle* out) {
     ellcuda_ctx* c = new ellcuda_ctx();
     c->device = h->device; c->n = h->n; c->w = h->w; c->c0 = h->c0;
     c->nseg = h->nseg; c->reduce_mode = h->reduce_mode; c->no_defer = h->no_defer; c->use_parallel = h->use_parallel;
-    c->sym = h->sym;
+    c->sym = h->sym; c->sym_rank = h->sym_rank; c->sym_count = h->sym_count;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     c->own_stream = true;
@@ -895,6 +903,22 @@ int ellcuda_kappa(ell_handle h, double* out) {
 
 int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row-major
     if (!h || !out) { set_error("null argument"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty() && h->parts[0]->sym) {   // symmetric group: every 64x64 tile from the slab that owns its column-block pair
+        const long long n = h->n, T = (n + 63) / 64;
+        const int P = (int)h->parts.size();
+        std::vector<double> tmp((size_t)n * n);
+        for (int r = 0; r < P; ++r) {
+            const int rc = ellcuda_get_mq(h->parts[r], tmp.data());
+            if (rc) return rc;
+            for (long long i = 0; i < n; ++i)
+                for (long long j = 0; j < n; ++j) {
+                    const long long J = (i < j ? i : j) / 64;            // column block of the stored (lower) tile
+                    const long long pair = J < T - 1 - J ? J : T - 1 - J;
+                    if (pair % P == r) out[i * n + j] = tmp[(size_t)i * n + j];
+                }
+        }
+        return ELLCUDA_OK;
+    }
     if (!h->parts.empty()) {   // group: the slabs in row order make up the whole matrix
         for (ellcuda_ctx* p : h->parts) { const int rc = ellcuda_get_mq(p, out + p->c0 * p->n); if (rc) return rc; }
         return ELLCUDA_OK;
@@ -934,6 +958,8 @@ int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row
 int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev) {
     if (!h || !x_dev || !y_dev) { set_error("null argument"); return ELLCUDA_E_ARG; }
     if (h->kind != ELL_KIND_ELL) { set_error("dot_mv needs an Ell handle"); return ELLCUDA_E_ARG; }
+    if (h->sym && h->sym_count > 1) { set_error("dot_mv is not available on a sharded symmetric-storage handle"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty() && h->parts[0]->sym) { set_error("dot_mv is not available on a sharded symmetric-storage handle"); return ELLCUDA_E_ARG; }
     if (!h->parts.empty()) {   // group: every device forms its rows of y from its own copy of x; y_dev receives all n entries
         for (ellcuda_ctx* p : h->parts) {
             ELL_DEVICE_SCOPE(p->device);
@@ -964,9 +990,13 @@ int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, do
         for (ellcuda_ctx* p : h->parts) {   // every slab's sweep is enqueued before any finish can start waiting for peers
             ELL_DEVICE_SCOPE(p->device);
             ELL_CUDA_TRY(cudaMemcpyAsync(p->gstage, grad_dev, (size_t)p->n * 8, cudaMemcpyDefault, p->stream));
-            const int rc = ellcuda_update_begin(p, which, p->gstage, beta0, has_beta1, beta1);
+            p->which = which;
+            p->cut = has_beta1 > 0 ? parallel_cut(beta0, beta1) : single_cut(beta0);
+            const int rc = enqueue_begin(p, p->gstage);
             if (rc) return rc;
         }
+        for (ellcuda_ctx* p : h->parts)   // sharded symmetric storage: phase 2 of the reduction only after every slab's phase 1 is enqueued
+            if (p->sym) { ELL_DEVICE_SCOPE(p->device); const int rc = sym_reduce(p); if (rc) return rc; }
         return ELLCUDA_OK;
     }
     ELL_DEVICE_SCOPE(h->device);
@@ -977,7 +1007,9 @@ int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, do
         return launch_stable_single(h->st_qu, h->xc, h->st_scal, h->st_status, grad_dev, (int)h->n, h->use_parallel, which, h->cut,
                                     h->stream);
     }
-    return enqueue_begin(h, grad_dev);
+    int rc = enqueue_begin(h, grad_dev);
+    if (rc == ELLCUDA_OK && h->sym && h->sym_count > 1) rc = sym_reduce(h);   // peers are other GPUs: their phase 1 runs concurrently
+    return rc;
 }
 
 int ellcuda_update_finish(ell_handle h) {
@@ -1045,13 +1077,7 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double 
     if (!h->parts.empty()) {   // group: host gradient to every device, all sweeps, all finishes, then the (identical) status
         nvtxRangePushA("ellcuda_update[group]");
         int rc = ELLCUDA_OK;
-        for (ellcuda_ctx* p : h->parts) {
-            DevGuard guard(p->device);
-            cudaError_t e = guard.err;
-            if (e == cudaSuccess) e = cudaMemcpyAsync(p->gstage, grad_host, (size_t)p->n * 8, cudaMemcpyHostToDevice, p->stream);
-            if (e != cudaSuccess) { rc = cuda_fail(e, "group gradient upload", __FILE__, __LINE__); break; }
-            if ((rc = ellcuda_update_begin(p, which, p->gstage, beta0, has_beta1, beta1))) break;
-        }
+        rc = ellcuda_update_begin(h, which, grad_host, beta0, has_beta1, beta1);   // cudaMemcpyDefault: a host pointer is fine
         if (!rc) rc = ellcuda_update_finish(h);
         if (!rc) rc = ellcuda_last_status(h, out_status);
         nvtxRangePop();
@@ -1110,7 +1136,10 @@ void* ellcuda_exchange_block_ptr(ell_handle h) { return h ? h->xblk : nullptr; }
 
 static int attach_common(ell_handle h, int32_t nranks, int32_t rank) {
     if (!h->parts.empty()) { set_error("a group handle manages its own exchange"); return ELLCUDA_E_ARG; }
-    if (h->sym) { set_error("symmetric storage does not shard rows"); return ELLCUDA_E_ARG; }
+    if (h->sym && (h->sym_count != nranks || h->sym_rank != rank)) {
+        set_error("a symmetric-storage handle attaches to exactly shard_count peers as rank shard_rank");
+        return ELLCUDA_E_ARG;
+    }
     if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) { set_error("bad nranks/rank"); return ELLCUDA_E_ARG; }
     if (h->nranks > 0) { set_error("exchange already attached"); return ELLCUDA_E_ARG; }
     ELL_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1175,8 +1204,13 @@ int ellcuda_create_sharded(const ell_create_desc* d, int32_t ndev, const int32_t
     for (int r = 0; r < ndev; ++r) {
         ell_create_desc dr = *d;
         dr.device = devs[r];
-        dr.row_begin = r * base + (r < rem ? r : rem);
-        dr.row_end = dr.row_begin + base + (r < rem ? 1 : 0);
+        if (d->storage == ELL_STORAGE_SYMMETRIC) {   // column-block pairs dealt round-robin, the exchange is a reduction
+            dr.row_begin = 0; dr.row_end = d->n;
+            dr.shard_rank = r; dr.shard_count = ndev;
+        } else {
+            dr.row_begin = r * base + (r < rem ? r : rem);
+            dr.row_end = dr.row_begin + base + (r < rem ? 1 : 0);
+        }
         dr.stream = nullptr;   // every slab runs on its own stream of its own device ...
         for (int q = 0; q < r; ++q)   // ... but slabs that share a device share ONE stream: a finish kernel waits for the other
             if (devs[q] == devs[r]) { dr.stream = g->parts[q]->stream; break; }   // slabs' sweeps, and kernels that wait on one

@@ -34,7 +34,7 @@ class Ell:
     KIND = _abi.KIND_ELL
 
     def __init__(self, kappa, xc, mq=None, diag=None, *, device=0, no_defer_trick=False, use_parallel_cut=True,
-                 rows=None, reduce_mode=0, stream=0, devices=None, storage=0, _handle=None):
+                 rows=None, reduce_mode=0, stream=0, devices=None, storage=0, shard=None, _handle=None):
         """devices=[d0, d1, …]: rows sharded over these devices of this process (ellcuda_create_sharded); the object is
         then used exactly like a single-device one."""
         self._keep = []
@@ -61,6 +61,8 @@ class Ell:
         d.reduce_mode = reduce_mode
         d.storage = storage          # 0 = full matrix (bit-identical), 1 = lower block-triangle only (half the traffic, 1e-9)
         d.stream = stream
+        if shard is not None:        # symmetric storage sharded over ranks: (rank, count)
+            d.shard_rank, d.shard_count = shard
         h = C.c_void_p()
         if devices is not None:
             devs = (C.c_int32 * len(devices))(*devices)

@@ -64,8 +64,14 @@ class ShardedEll:
         self.n = n
         self.device = torch.cuda.current_device() if device is None else device
         self.lo, self.hi = shard_range(n, self.rank, self.world)
-        self.ell = Ell(kappa, xc, mq=mq, diag=diag, device=self.device, no_defer_trick=no_defer_trick,
-                       use_parallel_cut=use_parallel_cut, rows=(self.lo, self.hi), reduce_mode=reduce_mode, storage=storage)
+        if storage:   # symmetric storage: column-block pairs dealt round-robin to the ranks, the exchange is a reduction (p2p only)
+            exchange = "p2p"
+            self.ell = Ell(kappa, xc, mq=mq, diag=diag, device=self.device, no_defer_trick=no_defer_trick,
+                           use_parallel_cut=use_parallel_cut, reduce_mode=reduce_mode, storage=storage,
+                           shard=(self.rank, self.world) if self.world > 1 else None)
+        else:
+            self.ell = Ell(kappa, xc, mq=mq, diag=diag, device=self.device, no_defer_trick=no_defer_trick,
+                           use_parallel_cut=use_parallel_cut, rows=(self.lo, self.hi), reduce_mode=reduce_mode)
         # run on torch's current stream so that the NCCL exchange is ordered with the sweeps; torch reports the legacy
         # default stream as handle 0, which the C ABI reads as "own stream" — cudaStreamLegacy (0x1) names it explicitly
         self.ell.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)

@@ -224,6 +224,10 @@ typedef struct ell_create_desc {
                                   M·g are regrouped, so results are held to 1e-9 relative, not bit-identical.  Whole
                                   matrix only (no row sharding), `mq` must be symmetric                          */
     void*   stream;            /* cudaStream_t; NULL ⇒ own stream, (void*)1 = cudaStreamLegacy */
+    int32_t shard_rank;        /* ELL_STORAGE_SYMMETRIC only: this handle keeps current the tiles of the column-block   */
+    int32_t shard_count;       /* pairs p ≡ shard_rank (mod shard_count) and the ranks REDUCE their partial grad_t over
+                                  NVLink after ellcuda_exchange_attach (0 or 1 ⇒ not sharded).  Full storage shards by
+                                  row_begin / row_end instead (a gather).  ellcuda_create_sharded sets these itself      */
 } ell_create_desc;
 
 int  ellcuda_create(const ell_create_desc* desc, ell_handle* out); /* Ell::new* src/ell.rs:31-78 */

@@ -58,6 +58,8 @@ pub struct ell_create_desc {
     pub reduce_mode: i32,
     pub storage: i32, // ELL_STORAGE_FULL = 0 (bit-identical), ELL_STORAGE_SYMMETRIC = 1 (half the HBM traffic, 1e-9)
     pub stream: *mut c_void,
+    pub shard_rank: i32,  // symmetric storage only: owner of the column-block pairs p = shard_rank (mod shard_count)
+    pub shard_count: i32, // 0 or 1 = not sharded
 }
 
 #[repr(C)]

@@ -56,6 +56,8 @@ impl<const KIND: i32> EllCudaT<KIND> {
             reduce_mode: 0,
             storage: 0,
             stream: std::ptr::null_mut(),
+            shard_rank: 0,
+            shard_count: 0,
         };
         let mut h: sys::ell_handle = std::ptr::null_mut();
         if devices.is_empty() {

@@ -36,6 +36,32 @@ for n, mode, xch in ((1024, 0, 'p2p'), (1000, 0, 'nccl'), (2048, 4, 'p2p'), (409
     r = s.state()
     ok &= bool(np.array_equal(slab, r["mq"][e.lo:e.hi]) if mode == 0 else np.abs(slab - r["mq"][e.lo:e.hi]).max() <= 1e-9)
     print(f"rank {rank}: n={n} mode={mode} exchange={xch} rows [{e.lo},{e.hi}) ok={ok}", flush=True)
+# symmetric storage sharded over the ranks (column-block pairs round-robin, reduction of flagged lines): 1e-9 gate, and each
+# rank's OWN tiles of M against the checker
+for n in (1024, 700):
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1, 1, (n, n)) / n
+    mq = np.eye(n) + a + a.T
+    xc = rng.uniform(-1, 1, n)
+    s = R.Space(A.KIND_ELL, n, kappa=1.0, mq=mq, xc=xc)
+    e = ShardedEll(1.0, xc, mq=mq, device=local, storage=A.STORAGE_SYMMETRIC)
+    good = True
+    for k in range(7):
+        g = W.large_n_grad(n, k)
+        beta = ParallelCut(0.01, 0.10) if k != 3 else ParallelCut(5.0, 4.0)
+        st = e.update(A.UPDATE_BIAS, torch.from_numpy(g).cuda(), beta)
+        st_r = s.update(0, g, beta.beta0, beta.beta1, single=False)
+        r = s.state()
+        good &= int(st) == st_r and abs(e.tsq() - r["tsq"]) <= 1e-9 * abs(r["tsq"]) and np.abs(e.xc() - r["xc"]).max() <= 1e-9 * np.abs(r["xc"]).max()
+    T = (n + 63) // 64
+    blk = np.arange(n) // 64
+    J = np.minimum(blk[:, None], blk[None, :])
+    mine = (np.minimum(J, T - 1 - J) % world) == rank
+    full, r = e.ell.mq, s.state()
+    good &= bool(np.abs(full - r["mq"])[mine].max() <= 1e-9 * np.abs(r["mq"]).max())
+    ok &= bool(good)
+    print(f"rank {rank}: n={n} symmetric storage sharded over {world} ranks ok={good}", flush=True)
+    del e
 # the configuration bench.py times at this world size: n = 16384, reduce_mode = world, p2p — first two updates from M = I
 # against the checker (rank 0 runs it: ~15 s per update on one core), every rank compares its scalars, xc and its slab of M
 if os.environ.get("ELL_MGC_LARGE", "1") != "0":

@@ -310,3 +310,27 @@ def test_symmetric_storage_drives_the_reference_loop():  # src/example1.rs:39-70
     e = Ell.new_with_scalar(10.0, np.zeros(2), storage=A.STORAGE_SYMMETRIC)
     xbest, niter, gamma = cutting_plane_optim(_Example1(), e, -math.inf, Options(tolerance=1e-10))
     assert xbest is not None and niter == 25
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0], [0, 1], [0, 1, 2, 3]])
+@pytest.mark.parametrize("n", [130, 1024])
+def test_symmetric_storage_group(ref, n, devices):
+    """symmetric storage sharded inside one process: column-block pairs dealt round-robin, the partial grad_t reduced over the slabs"""
+    if max(devices) >= _ndev():
+        pytest.skip("needs more GPUs in this process")
+    kw = _start(n, "matrix", 41)
+    e = Ell(kw["kappa"], kw["xc"], mq=kw["mq"], devices=devices, storage=A.STORAGE_SYMMETRIC)
+    s = ref.Space(A.KIND_ELL, n, kappa=kw["kappa"], mq=kw["mq"], xc=kw["xc"])
+    assert np.array_equal(e.mq, kw["mq"])
+    for k, (which, g, cut) in enumerate(_cuts(n, 10, 29)):
+        st_g, st_r = _gpu_update(e, which, g, cut), _ref_update(s, which, g, cut)
+        r = s.state()
+        assert int(st_g) == st_r, f"step {k}"
+        assert rel_err(e.tsq(), r["tsq"]).max() <= REL_TOL and rel_err(e.kappa, r["kappa"]).max() <= REL_TOL, f"step {k}"
+        assert np.abs(e.xc() - r["xc"]).max() <= REL_TOL * np.abs(r["xc"]).max(), f"step {k}"
+        if k == 6:
+            c, sc = e.clone(), s.clone()
+    assert np.abs(e.mq - r["mq"]).max() <= REL_TOL * np.abs(r["mq"]).max()
+    which, g, cut = _cuts(n, 10, 29)[7]
+    assert int(_gpu_update(c, which, g, cut)) == _ref_update(sc, which, g, cut)
+    assert np.abs(c.xc() - sc.state()["xc"]).max() <= REL_TOL * np.abs(sc.state()["xc"]).max()
