@@ -221,8 +221,9 @@ typedef struct ell_create_desc {
     int32_t storage;           /* ELL_STORAGE_FULL (0): the full mirrored matrix as the reference holds it; results
                                   bit-identical in reduce_mode 0.  ELL_STORAGE_SYMMETRIC (1): only the lower
                                   block-triangle is kept and streamed — half the HBM traffic per update; the sums of
-                                  M·g are regrouped, so results are held to 1e-9 relative, not bit-identical.  Whole
-                                  matrix only (no row sharding), `mq` must be symmetric                          */
+                                  M·g are regrouped, so results are held to 1e-9 relative, not bit-identical.  `mq`
+                                  must be symmetric; shards by shard_rank / shard_count below (or through
+                                  ellcuda_create_sharded), not by rows                                            */
     void*   stream;            /* cudaStream_t; NULL ⇒ own stream, (void*)1 = cudaStreamLegacy */
     int32_t shard_rank;        /* ELL_STORAGE_SYMMETRIC only: this handle keeps current the tiles of the column-block   */
     int32_t shard_count;       /* pairs p ≡ shard_rank (mod shard_count) and the ranks REDUCE their partial grad_t over
