@@ -209,35 +209,62 @@ __global__ void __launch_bounds__(64) sym_sweep_kernel(const __grid_constant__ C
     else sym_body<true, true>(a, &map, ring, ch, pre, scale);
 }
 
-// grad_t[i] = (column sums of block B = i/64, segment slots in order) + (row sums rowpart[J][i], J = 0..B-1 in order)
-__global__ void __launch_bounds__(256) sym_combine_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
-                                                          double* __restrict__ out, long long n, long long npad, int nseg) {
+// grad_t[i] = (column sums of block B = i/64: segment slots in order) + (row sums rowpart[J][i], J = 0..B-1), in a FIXED order:
+// a CTA of 8 warps handles 32 consecutive elements; warp w adds its eighth of the J range in order (coalesced 256-byte loads,
+// several in flight), warp 0 then adds the segment slots and the eight parts in order.  (One thread per element walking all
+// B <= 255 row blocks took 41 us at n = 16384: a chain of dependent L2 round trips.)
+constexpr int kCombThreads = 256;
+__device__ __forceinline__ double sym_partial(const double* __restrict__ colpart, const double* __restrict__ rowpart, long long n,
+                                              long long npad, int nseg, double* parts /* shared, 8 x 32 */, int T = 0, int rank = 0,
+                                              int count = 1) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + lane;
+    const int B = (int)(((long long)blockIdx.x * 32) >> 6);   // the same row block for all 32 elements
+    const int per = (B + 7) / 8;
+    const int j0 = w * per, j1 = j0 + per < B ? j0 + per : B;
+    double acc = 0.0;
+    if (i < n) {
+#pragma unroll 8
+        for (int J = j0; J < j1; ++J) {
+            if (count > 1) {   // sharded: row blocks of column blocks this rank does not own hold exact zeros — skip them
+                const int pr = J < T - 1 - J ? J : T - 1 - J;
+                if (pr % count != rank) continue;
+            }
+            acc += __ldcg(rowpart + (long long)J * npad + i);
+        }
+    }
+    parts[w * 32 + lane] = acc;
+    __syncthreads();
+    double s = 0.0;
+    if (w == 0 && i < n) {
+        for (int k = 0; k < nseg; ++k) s += __ldcg(colpart + (long long)k * npad + i);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += parts[q * 32 + lane];
+    }
+    return s;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(kCombThreads) sym_combine_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
+                                                                   double* __restrict__ out, long long n, long long npad, int nseg) {
+    __shared__ double parts[8 * 32];
     pdl_trigger();
     pdl_wait();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int B = (int)(i >> 6);
-    double s = 0.0;
-    for (int k = 0; k < nseg; ++k) s += __ldcg(colpart + (long long)k * npad + i);
-#pragma unroll 4
-    for (int J = 0; J < B; ++J) s += __ldcg(rowpart + (long long)J * npad + i);
-    out[i] = s;
+    const double s = sym_partial(colpart, rowpart, n, npad, nseg, parts);
+    const long long i = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+    if (threadIdx.x < 32 && i < n) out[i] = s;
 }
 
 // Sharded symmetric storage: every rank has partial sums for ALL n elements (from its tiles), so the exchange is a reduction.
 // Phase 1 (this kernel): element i's local partial goes, as a flagged line, to the rank that reduces i (slices of `slice`).
-__global__ void __launch_bounds__(256) sym_combine_push_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
-                                                               long long n, long long npad, int nseg, PeerTable pt, const Scal* sc,
-                                                               long long slice) {
+__global__ void __launch_bounds__(kCombThreads) sym_combine_push_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
+                                                                        long long n, long long npad, int nseg, PeerTable pt, const Scal* sc,
+                                                                        long long slice) {
+    __shared__ double parts[8 * 32];
     pdl_trigger();
     pdl_wait();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || sc->failed) return;
-    const int B = (int)(i >> 6);
-    double s = 0.0;
-    for (int k = 0; k < nseg; ++k) s += __ldcg(colpart + (long long)k * npad + i);
-#pragma unroll 4
-    for (int J = 0; J < B; ++J) s += __ldcg(rowpart + (long long)J * npad + i);
+    const double s = sym_partial(colpart, rowpart, n, npad, nseg, parts, (int)(npad >> 6), pt.rank, pt.nranks);
+    const long long i = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+    if (threadIdx.x >= 32 || i >= n || sc->failed) return;
     const unsigned long long epoch = sc->epoch;
     const int o = (int)(i / slice);
     ll_store(xblk_parts(pt.blk[o], n, (int)(epoch & 1ULL), pt.nranks, pt.rank, slice) + (i - (long long)o * slice), s, (unsigned)epoch);
@@ -380,7 +407,7 @@ int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_o
         pt.nranks = h->nranks; pt.rank = h->rank;
         for (int r = 0; r < kMaxRanks; ++r) pt.blk[r] = r < h->nranks ? h->peer_blk[r] : nullptr;
         cudaLaunchConfig_t cc{};
-        cc.gridDim = dim3((unsigned)((h->n + 255) / 256)); cc.blockDim = dim3(256); cc.dynamicSmemBytes = 0; cc.stream = s;
+        cc.gridDim = dim3((unsigned)((h->n + 31) / 32)); cc.blockDim = dim3(kCombThreads); cc.dynamicSmemBytes = 0; cc.stream = s;
         cc.attrs = attr; cc.numAttrs = pdl_enabled() ? 1 : 0;
         ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_combine_push_kernel, (const double*)h->colpart, (const double*)h->rowpart, h->n, a.npad,
                                         a.nseg, pt, (const Scal*)h->sc, h->sym_slice));
@@ -388,7 +415,7 @@ int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_o
         return ELLCUDA_OK;
     }
     cudaLaunchConfig_t cc{};
-    cc.gridDim = dim3((unsigned)((h->n + 255) / 256)); cc.blockDim = dim3(256); cc.dynamicSmemBytes = 0; cc.stream = s;
+    cc.gridDim = dim3((unsigned)((h->n + 31) / 32)); cc.blockDim = dim3(kCombThreads); cc.dynamicSmemBytes = 0; cc.stream = s;
     cc.attrs = attr; cc.numAttrs = pdl_enabled() ? 1 : 0;
     ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_combine_kernel, (const double*)h->colpart, (const double*)h->rowpart,
                                     plain_out ? plain_out : h->xblk, h->n, a.npad, a.nseg));
