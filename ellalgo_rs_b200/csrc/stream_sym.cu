@@ -237,7 +237,8 @@ __device__ __forceinline__ double sym_partial(const double* __restrict__ colpart
     __syncthreads();
     double s = 0.0;
     if (w == 0 && i < n) {
-        for (int k = 0; k < nseg; ++k) s += __ldcg(colpart + (long long)k * npad + i);
+#pragma unroll 8
+        for (int k = 0; k < nseg; ++k) s += __ldcg(colpart + (long long)k * npad + i);   // unrolled: the loads go out together, the adds stay in order
 #pragma unroll
         for (int q = 0; q < 8; ++q) s += parts[q * 32 + lane];
     }
@@ -281,15 +282,27 @@ __global__ void __launch_bounds__(256) sym_reduce_kernel(long long n, PeerTable 
     const unsigned long long epoch = sc->epoch;
     const int par = (int)(epoch & 1ULL);
     const unsigned flag = (unsigned)epoch;
-    double t = 0.0;
-    for (int r = 0; r < pt.nranks; ++r) {
-        double v = 0.0;
-        if (!ll_load(xblk_parts(pt.blk[pt.rank], n, par, pt.nranks, r, slice) + j, flag, v)) {
-            atomicExch(&sc->failed, 1);   // a peer never delivered: the handle is dead (finish reports Unknown from now on)
-            return;
+    // all P lines are requested before any is checked (one round trip instead of P); a line that has not arrived yet is polled
+    unsigned wds[kMaxRanks][4];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (r < pt.nranks) {
+            const uint4* line = xblk_parts(pt.blk[pt.rank], n, par, pt.nranks, r, slice) + j;
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wds[r][0]), "=r"(wds[r][1]), "=r"(wds[r][2]), "=r"(wds[r][3]) : "l"(line) : "memory");
         }
-        t += v;
-    }
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (r < pt.nranks) {
+            double v = __hiloint2double((int)wds[r][2], (int)wds[r][0]);
+            if (wds[r][1] != flag || wds[r][3] != flag) {
+                if (!ll_load(xblk_parts(pt.blk[pt.rank], n, par, pt.nranks, r, slice) + j, flag, v)) {
+                    atomicExch(&sc->failed, 1);   // a peer never delivered: the handle is dead (finish reports Unknown from now on)
+                    return;
+                }
+            }
+            t += v;   // rank order
+        }
     for (int r = 0; r < pt.nranks; ++r) ll_store(xblk_lines(pt.blk[r], n, par) + i, t, flag);
 }
 
@@ -320,7 +333,7 @@ int sym_alloc(ellcuda_ctx* h) {
     h->sym_slice = (h->n + h->sym_count - 1) / h->sym_count;
     int nseg = h->reduce_mode > 0 ? h->reduce_mode : (int)((256 + npairs - 1) / npairs);   // ~256 streaming CTAs
     if (nseg < 1) nseg = 1;
-    if (nseg > 16) nseg = 16;
+    if (nseg > 16) nseg = 16;   // measured on the 8-way emulation (tools/profile_symslab.py): 8 -> 119 us per rank, 12 -> 93, 16 -> 82.5, 24 -> 100, 32 -> 92
     h->sym_nseg = nseg;
     const size_t tiles = (size_t)tile_index(h->T - 1, h->T - 1) + 1;
     ELL_CUDA_TRY(cudaMalloc(&h->Mp, tiles * kTileBytes));

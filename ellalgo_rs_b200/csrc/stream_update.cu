@@ -325,13 +325,18 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         }
 #pragma unroll 4
         for (; k < n; k += kFinThreads) acc += g[k] * load_gt(k);
-        prod[tid] = acc;
+        // fixed tree: xor-shuffles inside each warp, the 32 warp sums through shared memory, xor-shuffles again (two barriers
+        // instead of ten; the same association on every rank)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if ((tid & 31) == 0) prod[tid >> 5] = acc;
         __syncthreads();
-        for (int off = kFinThreads / 2; off > 0; off >>= 1) {
-            if (tid < off) prod[tid] = prod[tid] + prod[tid + off];
-            __syncthreads();
+        if (tid < 32) {
+            double v = prod[tid];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (tid == 0) s_omega = v;
         }
-        if (tid == 0) s_omega = prod[0];
     }
     if (lost) {
         s_timeout = 1;
