@@ -48,3 +48,43 @@ def run_stepwise(make_space, update, state):
         update(s, 0, W.large_n_grad(n, k), *W.LARGE_N_CUT)
     st = state(s)
     return {"xc": st["xc"], "mq": st["mq"], "kappa": np.array(st["kappa"]), "tsq": np.array(st["tsq"])}
+
+
+# ---------------------------------------------------------------------------------- round 2: tests/golden/golden_v2.npz
+def _asym_batch(n, count, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(scale * (np.eye(n)[None] + rng.uniform(-1, 1, (count, n, n)) / (2 * n)))
+
+
+def _with(p, **kw):
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+CASES_V2 = {
+    "bowl48": lambda R: W.bowl(6, n=48, max_iters=3000),                                   # M in tensor memory (batch_ell64.cu)
+    "bowl64_nonsym": lambda R: _with(W.bowl(5, n=64, max_iters=600), mq0=_asym_batch(64, 5, 11, 100.0), kappa0=np.ones(1)),
+    "bowl32_nonsym": lambda R: _with(W.bowl(5, n=32, max_iters=600), mq0=_asym_batch(32, 5, 12, 100.0), kappa0=np.ones(1)),
+    "lowpass40": lambda R: W.lowpass(3, R.lowpass_table(40), n=40, max_iters=2500),
+    "lmi_on_ell": lambda R: _with(W.lmi(6, n=64, m=16), kind=A.KIND_ELL),                 # tests/lmi_tests.rs:174-206 run both spaces
+    "lmi0_on_ell": lambda R: _with(W.lmi0(5, n=64, m=16), kind=A.KIND_ELL),
+    "profit_nonsym": lambda R: _with(W.profit(8), diag0=None, mq0=np.ascontiguousarray(
+        np.array([[100.0, 1.5], [-0.75, 100.0]])[None] * np.ones((8, 1, 1)))),
+}
+
+
+def run_stepwise_nonsym(make_space, update, state):
+    """an n=40 Ell from a NON-symmetric matrix: two failing cuts first (rows multiplied as given, nothing mirrored), then four
+    successful ones (the first rewrites the upper triangle from the lower one, src/ell.rs:117-128); returns the final state."""
+    n = 40
+    rng = np.random.default_rng(321)
+    mq = np.eye(n) + rng.uniform(-1, 1, (n, n)) / (2 * n)
+    s = make_space(n=n, kappa=1.25, mq=mq, xc=rng.uniform(-1, 1, n))
+    update(s, 0, W.large_n_grad(n, 0), 5.0, 4.0)          # beta1 < beta0: NoSoln
+    update(s, 0, W.large_n_grad(n, 1), 1e6, 2e6)          # tsq < beta^2: NoSoln
+    mid = state(s)
+    for k in range(2, 6):
+        update(s, 0, W.large_n_grad(n, k), *W.LARGE_N_CUT)
+    st = state(s)
+    return {"xc": st["xc"], "mq": st["mq"], "kappa": np.array(st["kappa"]), "tsq": np.array(st["tsq"]), "mq_before_first_success": mid["mq"]}

@@ -6,15 +6,17 @@ import numpy as np
 import pytest
 
 from ellalgo_rs_b200 import _abi as A
-from golden_cases import CASES, run_stepwise
+from golden_cases import CASES, CASES_V2, run_stepwise, run_stepwise_nonsym
 
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+GOLD2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
 FIELDS = ("xbest", "has_xbest", "num_iters", "exit_status", "gamma", "tsq", "xc", "kappa")
 
 
-def _check(name, o):
+def _check(name, o, gold=None):
+    gold = GOLD if gold is None else gold
     for f in FIELDS:
-        assert np.array_equal(getattr(o, f), GOLD[f"{name}/{f}"], equal_nan=True), f"{name}/{f} differs from the golden vector"
+        assert np.array_equal(getattr(o, f), gold[f"{name}/{f}"], equal_nan=True), f"{name}/{f} differs from the golden vector"
 
 
 def test_golden_has_the_pinned_counts():
@@ -50,3 +52,36 @@ def test_cuda_stepwise_golden():
                       lambda s: dict(xc=s.xc(), mq=s.mq, kappa=s.kappa, tsq=s.tsq()))
     for k, v in st.items():
         assert np.array_equal(v, GOLD[f"stepwise/{k}"])
+
+
+# ---------------------------------------------------------------- round 2 vectors (golden_v2.npz)
+@pytest.mark.parametrize("name", list(CASES_V2))
+def test_checker_reproduces_golden_v2(ref, name):
+    _check(name, ref.solve(CASES_V2[name](ref)), GOLD2)
+
+
+def test_checker_stepwise_nonsym_golden(ref):
+    st = run_stepwise_nonsym(lambda **kw: ref.Space(A.KIND_ELL, **kw), lambda s, w, g, b0, b1: s.update(w, g, b0, b1, single=False),
+                             lambda s: s.state())
+    for k, v in st.items():
+        assert np.array_equal(v, GOLD2[f"stepwise_nonsym/{k}"])
+    assert not np.array_equal(GOLD2["stepwise_nonsym/mq_before_first_success"], GOLD2["stepwise_nonsym/mq_before_first_success"].T)
+    assert np.array_equal(GOLD2["stepwise_nonsym/mq"], GOLD2["stepwise_nonsym/mq"].T)      # mirrored by the first successful cut
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES_V2))
+def test_cuda_reproduces_golden_v2(ref, name):
+    from ellalgo_rs_b200 import batch
+    _check(name, batch.solve_batch(CASES_V2[name](ref)), GOLD2)
+
+
+@pytest.mark.gpu
+def test_cuda_stepwise_nonsym_golden():
+    from ellalgo_rs_b200.cutting_plane import ParallelCut
+    from ellalgo_rs_b200.ell import Ell
+    st = run_stepwise_nonsym(lambda n, kappa, mq, xc: Ell(kappa, xc, mq=mq),
+                             lambda s, w, g, b0, b1: s.update_bias_cut((g, ParallelCut(b0, b1))),
+                             lambda s: dict(xc=s.xc(), mq=s.mq, kappa=s.kappa, tsq=s.tsq()))
+    for k, v in st.items():
+        assert np.array_equal(v, GOLD2[f"stepwise_nonsym/{k}"])
