@@ -380,7 +380,7 @@ def main():
             a1.record(stream)
             barrier()
             t_large = max_over_ranks(a0.elapsed_time(a1) / 1e3)
-            per_update = (3 + (2 if world > 1 else 0)) if storage else 2    # sym: sweep, combine(+push), [reduce,] finish
+            per_update = 3 if storage else 2    # sym: sweep, combine (sharded: + push, reduce and broadcast of the slice), finish
             l_launch = (per_update * LARGE_UPDATES) if graph is not None else ell.ell.launches - l0
             status = int(ell.ell.last_status())
             kind = ell.exchange_kind

@@ -265,6 +265,7 @@ struct ellcuda_ctx {
     int sym_nseg = 1;
     int sym_rank = 0, sym_count = 1;   // sharded symmetric storage: this handle keeps the pairs p = sym_rank (mod sym_count) current
     long long sym_slice = 0;    // ceil(n / sym_count): the elements of grad_t this rank reduces
+    bool sym_fused = false;     // peers are other processes / GPUs (IPC attach): the combine kernel also reduces and broadcasts its slice
     std::vector<ellcuda_ctx*> parts;
     double* ytmp = nullptr;     // group members: slab of a dot_mv result before it is copied to the caller's vector
     int which = 0;

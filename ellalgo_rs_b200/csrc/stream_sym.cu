@@ -257,8 +257,13 @@ __global__ void __launch_bounds__(kCombThreads) sym_combine_kernel(const double*
 
 // Sharded symmetric storage: every rank has partial sums for ALL n elements (from its tiles), so the exchange is a reduction.
 // Phase 1 (this kernel): element i's local partial goes, as a flagged line, to the rank that reduces i (slices of `slice`).
+// FUSED (the peers are other GPUs, attached by IPC): the thread whose element lies in this rank's slice goes straight on to
+// phase 2 — it depends only on its own store and on the other GPUs' kernels, never on a later launch of this GPU.
+__device__ __forceinline__ void sym_reduce_one(long long n, const PeerTable& pt, Scal* sc, long long slice, long long j, unsigned long long epoch);
+
+template <bool FUSED>
 __global__ void __launch_bounds__(kCombThreads) sym_combine_push_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
-                                                                        long long n, long long npad, int nseg, PeerTable pt, const Scal* sc,
+                                                                        long long n, long long npad, int nseg, PeerTable pt, Scal* sc,
                                                                         long long slice) {
     __shared__ double parts[8 * 32];
     pdl_trigger();
@@ -269,17 +274,13 @@ __global__ void __launch_bounds__(kCombThreads) sym_combine_push_kernel(const do
     const unsigned long long epoch = sc->epoch;
     const int o = (int)(i / slice);
     ll_store(xblk_parts(pt.blk[o], n, (int)(epoch & 1ULL), pt.nranks, pt.rank, slice) + (i - (long long)o * slice), s, (unsigned)epoch);
+    if (FUSED && o == pt.rank) sym_reduce_one(n, pt, sc, slice, i - (long long)o * slice, epoch);
 }
 
 // Phase 2: this rank's slice — the P partials in rank order (identical on every rank by construction: one rank does it),
 // then the sum as a flagged line into every rank's grad_t lines, which finish_kernel polls as for a gathered exchange.
-__global__ void __launch_bounds__(256) sym_reduce_kernel(long long n, PeerTable pt, Scal* sc, long long slice) {
-    pdl_trigger();
-    pdl_wait();
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void sym_reduce_one(long long n, const PeerTable& pt, Scal* sc, long long slice, long long j, unsigned long long epoch) {
     const long long i = (long long)pt.rank * slice + j;
-    if (j >= slice || i >= n || sc->failed) return;
-    const unsigned long long epoch = sc->epoch;
     const int par = (int)(epoch & 1ULL);
     const unsigned flag = (unsigned)epoch;
     // all P lines are requested before any is checked (one round trip instead of P); a line that has not arrived yet is polled
@@ -304,6 +305,14 @@ __global__ void __launch_bounds__(256) sym_reduce_kernel(long long n, PeerTable 
             t += v;   // rank order
         }
     for (int r = 0; r < pt.nranks; ++r) ll_store(xblk_lines(pt.blk[r], n, par) + i, t, flag);
+}
+
+__global__ void __launch_bounds__(256) sym_reduce_kernel(long long n, PeerTable pt, Scal* sc, long long slice) {
+    pdl_trigger();
+    pdl_wait();
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= slice || (long long)pt.rank * slice + j >= n || sc->failed) return;
+    sym_reduce_one(n, pt, sc, slice, j, sc->epoch);
 }
 
 __global__ void sym_fill_diag_kernel(double* __restrict__ Mp, long long n, const double* __restrict__ diag) {
@@ -422,8 +431,12 @@ int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_o
         cudaLaunchConfig_t cc{};
         cc.gridDim = dim3((unsigned)((h->n + 31) / 32)); cc.blockDim = dim3(kCombThreads); cc.dynamicSmemBytes = 0; cc.stream = s;
         cc.attrs = attr; cc.numAttrs = pdl_enabled() ? 1 : 0;
-        ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_combine_push_kernel, (const double*)h->colpart, (const double*)h->rowpart, h->n, a.npad,
-                                        a.nseg, pt, (const Scal*)h->sc, h->sym_slice));
+        if (h->sym_fused)
+            ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_combine_push_kernel<true>, (const double*)h->colpart, (const double*)h->rowpart, h->n,
+                                            a.npad, a.nseg, pt, h->sc, h->sym_slice));
+        else
+            ELL_CUDA_TRY(cudaLaunchKernelEx(&cc, sym_combine_push_kernel<false>, (const double*)h->colpart, (const double*)h->rowpart, h->n,
+                                            a.npad, a.nseg, pt, h->sc, h->sym_slice));
         h->launches += 1;
         return ELLCUDA_OK;
     }
@@ -437,7 +450,7 @@ int sym_sweep(ellcuda_ctx* h, const double* g_dev, int exchange, double* plain_o
 }
 
 int sym_reduce(ellcuda_ctx* h) {
-    if (h->sym_count <= 1) return ELLCUDA_OK;
+    if (h->sym_count <= 1 || h->sym_fused) return ELLCUDA_OK;   // fused: the combine kernel already did it
     PeerTable pt;
     pt.nranks = h->nranks; pt.rank = h->rank;
     for (int r = 0; r < kMaxRanks; ++r) pt.blk[r] = r < h->nranks ? h->peer_blk[r] : nullptr;

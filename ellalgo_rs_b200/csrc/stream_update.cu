@@ -1253,6 +1253,7 @@ int ellcuda_exchange_attach(ell_handle h, int32_t nranks, int32_t rank, const vo
         h->peer_opened[r] = true;
     }
     h->nranks = nranks; h->rank = rank;
+    h->sym_fused = h->sym && nranks > 1;   // IPC peers are other processes on other GPUs: phase 2 of the reduction can run in the same kernel
     return ELLCUDA_OK;
 }
 

@@ -295,7 +295,8 @@ double*  ellcuda_grad_t_ptr(ell_handle h);   /* device, n doubles: grad_t of han
  * same process; used to emulate ranks on one GPU, all on ONE stream, begin for every rank before any finish).     */
 #define ELLCUDA_IPC_HANDLE_BYTES 64
 int   ellcuda_exchange_export(ell_handle h, void* handle_out);
-int   ellcuda_exchange_attach(ell_handle h, int32_t nranks, int32_t rank, const void* handles /* nranks x 64 B */);
+int   ellcuda_exchange_attach(ell_handle h, int32_t nranks, int32_t rank, const void* handles /* nranks x 64 B; one rank per GPU:
+                                kernels of different ranks wait for each other's stores and must be able to run at the same time */);
 int   ellcuda_exchange_attach_ptrs(ell_handle h, int32_t nranks, int32_t rank, void* const* blocks);
 void* ellcuda_exchange_block_ptr(ell_handle h);
 int32_t* ellcuda_status_ptr(ell_handle h);   /* device, CutStatus of the last finish       */
