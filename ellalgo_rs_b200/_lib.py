@@ -22,7 +22,7 @@ EXPORTS = [
     "ellcuda_set_timing", "ellcuda_last_sweep_ms", "ellcuda_handle_launch_count",
     "ellcuda_math_probe", "ellcuda_last_error", "ellcuda_version", "ellcuda_device_count",
     "ellcuda_batch_solve_multi", "ellcuda_create_sharded", "ellcuda_group_size",
-    "ellcuda_set_no_defer_trick", "ellcuda_set_use_parallel_cut",
+    "ellcuda_set_no_defer_trick", "ellcuda_set_use_parallel_cut", "ellcuda_seq_sum",
 ]
 
 
@@ -95,6 +95,8 @@ def lib():
             getattr(L, name).restype = C.c_int
         L.ellcuda_dot_mv.argtypes = [H, C.c_void_p, C.c_void_p]
         L.ellcuda_dot_mv.restype = C.c_int
+        L.ellcuda_seq_sum.argtypes = [H, C.c_void_p, C.c_int64, _pd]
+        L.ellcuda_seq_sum.restype = C.c_int
         L.ellcuda_update.argtypes = [H, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_double, _pi]
         L.ellcuda_update.restype = C.c_int
         L.ellcuda_update_begin.argtypes = [H, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_double]

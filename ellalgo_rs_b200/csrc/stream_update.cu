@@ -590,6 +590,22 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev, double* plain_out = nullp
 
 __global__ void clear_pending_kernel(Scal* sc) { sc->pending = 0; sc->scale = 1.0; }
 
+// sum of v[0..n) strictly left to right from 0.0 (Arr::dot / Arr::sum order, src/arr.rs:443-451): the chunks are staged in
+// shared memory by the whole CTA, one thread walks the chain (10 clocks per element: the FP64 add latency)
+__global__ void __launch_bounds__(1024) seq_sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
+    __shared__ double buf[4096];
+    double acc = 0.0;
+    for (long long base = 0; base < n; base += 4096) {
+        const int len = (int)((n - base) < 4096 ? (n - base) : 4096);
+        for (int k = threadIdx.x; k < len; k += 1024) buf[k] = v[base + k];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int k = 0; k < len; ++k) acc += buf[k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = acc;
+}
+
 int flush_pending(ellcuda_ctx* h) {  // make S hold the reference's `mq` exactly
     int rc = enqueue_begin(h, nullptr);
     if (rc) return rc;
@@ -957,6 +973,26 @@ int ellcuda_get_mq(ell_handle h, double* out) {  // this slab's rows, w × n row
     cudaFreeAsync(tmp, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return cuda_fail(e, "ellcuda_get_mq", __FILE__, __LINE__);
+    return ELLCUDA_OK;
+}
+
+// Sequential (left-to-right) sum of a device vector on the handle's device and stream; synchronous, the result comes back to the
+// host.  With elementwise products formed by the caller this is Arr::dot (src/arr.rs:443-451) / the norms of
+// src/power_iteration.rs:22-25 for vectors that stay on the device between two ellcuda_dot_mv calls.
+int ellcuda_seq_sum(ell_handle h, const double* v_dev, int64_t n, double* out_host) {
+    if (!h || !out_host || n < 0 || (n > 0 && !v_dev)) { set_error("bad arguments"); return ELLCUDA_E_ARG; }
+    if (!h->parts.empty()) h = h->parts[0];
+    ELL_DEVICE_SCOPE(h->device);
+    if (n == 0) { *out_host = 0.0; return ELLCUDA_OK; }
+    double* d = nullptr;
+    ELL_CUDA_TRY(cudaMallocAsync((void**)&d, 8, h->stream));
+    seq_sum_kernel<<<1, 1024, 0, h->stream>>>(v_dev, n, d);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaFreeAsync(d, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ellcuda_seq_sum", __FILE__, __LINE__);
     return ELLCUDA_OK;
 }
 

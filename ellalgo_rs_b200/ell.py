@@ -188,9 +188,27 @@ class Ell:
     def dot_mv_device(self, x_dev_ptr: int, y_dev_ptr: int):
         check(lib().ellcuda_dot_mv(self._h, x_dev_ptr, y_dev_ptr))
 
-    def dot_mv(self, x) -> np.ndarray:
-        """y = mq·x for a host vector (H2D, streaming GEMV, D2H); sums in the reference's order"""
+    def seq_sum(self, v_dev) -> float:
+        """sum of a CUDA tensor strictly left to right (the reference's Arr::dot / sum order) on this handle's device"""
         import torch
+        torch.cuda.current_stream(self.device).synchronize()          # v_dev was produced on torch's stream
+        out = C.c_double()
+        check(lib().ellcuda_seq_sum(self._h, v_dev.data_ptr(), v_dev.numel(), C.byref(out)))
+        return out.value
+
+    def dot_mv(self, x):
+        """y = mq·x; sums in the reference's order.  A host vector goes H2D / streaming GEMV / D2H; a CUDA tensor on this
+        handle's device stays on the device and a CUDA tensor comes back (linalg.py keeps whole iterations on the GPU that way)"""
+        import torch
+        if isinstance(x, torch.Tensor):
+            if x.dtype != torch.float64 or x.numel() != self.n or x.device.index != self.device:
+                raise ValueError("x must be a float64 CUDA tensor of n entries on the handle's device")
+            x = x.contiguous()
+            y = torch.empty(self.n if self.group_size > 1 else self.rows[1] - self.rows[0], dtype=torch.float64, device=x.device)
+            torch.cuda.current_stream(self.device).synchronize()      # x may have been produced on torch's stream
+            self.dot_mv_device(x.data_ptr(), y.data_ptr())
+            self.sync()
+            return y
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.shape != (self.n,):
             raise ValueError("x must have n entries")  # assert_eq!(self.cols, x.len())

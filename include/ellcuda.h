@@ -263,6 +263,10 @@ int ellcuda_get_mq(ell_handle h, double* out_rows_by_n);  /* pub field Ell::mq (
  * The streaming GEMV that power_iteration (src/power_iteration.rs) and conjugate_gradient
  * (src/conjugate_gradient.rs) share with Ell::update_core.  Ell handles only.                                       */
 int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev);
+/* sum of v_dev[0..n) strictly left to right from 0.0 on the handle's device and stream; synchronous, result on the host.  With
+ * the elementwise product formed by the caller this is Arr::dot (src/arr.rs:443-451) and the norms of
+ * src/power_iteration.rs:22-25 for vectors that stay on the device between two ellcuda_dot_mv calls.                  */
+int ellcuda_seq_sum(ell_handle h, const double* v_dev, int64_t n, double* out_host);
 
 /* SearchSpace::update_{bias_cut,central_cut,q} with SingleCut(beta0) [has_beta1 = -1],
  * ParallelCut(beta0, None) [0] or ParallelCut(beta0, Some(beta1)) [1]

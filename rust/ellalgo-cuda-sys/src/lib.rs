@@ -114,6 +114,7 @@ extern "C" {
     pub fn ellcuda_create_sharded(desc: *const ell_create_desc, ndev: i32, devs: *const i32, out: *mut ell_handle) -> c_int;
     pub fn ellcuda_group_size(h: ell_handle) -> i32;
     pub fn ellcuda_batch_solve_multi(desc: *const ell_batch_desc, res: *const ell_batch_result, ndev: i32, devs: *const i32) -> c_int;
+    pub fn ellcuda_seq_sum(h: ell_handle, v_dev: *const f64, n: i64, out_host: *mut f64) -> c_int;
     pub fn ellcuda_set_no_defer_trick(h: ell_handle, on: i32) -> c_int;
     pub fn ellcuda_set_use_parallel_cut(h: ell_handle, on: i32) -> c_int;
     pub fn ellcuda_clone(h: ell_handle, out: *mut ell_handle) -> c_int;
