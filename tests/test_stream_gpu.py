@@ -424,10 +424,10 @@ def test_dot_mv_and_its_users_on_the_device(ref):
     assert np.array_equal(x, xr)
     e, it, xv = LA.power_iteration2(m, x0, LA.Options(300, 1e-10), device=True)
     assert (it, e) == (itr, er) and np.array_equal(xv, xvr)
-    for v, f, tol in ((1, LA.power_iteration, 1e-9), (4, LA.power_iteration4, 1e-9), (3, LA.power_iteration3, 1e-12)):
+    for variant, f, tol in ((1, LA.power_iteration, 1e-9), (4, LA.power_iteration4, 1e-9), (3, LA.power_iteration3, 1e-12)):
         e, it, xv = f(m, x0, LA.Options(200, tol), device=True)
-        er2, itr2, xvr2 = ref.power_iteration(v, spd, x0, 200, tol)
-        assert (it, e) == (itr2, er2) and np.array_equal(xv, xvr2), v
+        er2, itr2, xvr2 = ref.power_iteration(variant, spd, x0, 200, tol)
+        assert (it, e) == (itr2, er2) and np.array_equal(xv, xvr2), variant
     import torch
     t = torch.from_numpy(rng.uniform(-1, 1, 5000)).cuda()
     assert m.seq_sum(t) == float(np.cumsum(t.cpu().numpy())[-1])
