@@ -318,6 +318,14 @@ def main():
     e2e_value = e2e_iters / t_e2e
     clocks = sampler.stop() if sampler else None
 
+    # ---------------------------------------------------------------- configs[0]: the reference's own CPU-runnable case (correctness)
+    ex1_prob = W.example1()
+    ex1_prob.device = local
+    ex1 = batch.solve_batch(ex1_prob)
+    example1 = {"workload": "configs[0]: src/example1.rs:39-50 through ellcuda_batch_solve", "num_iters": int(ex1.num_iters[0]),
+                "reference_pin": 25, "exit_status": A.EXIT_NAMES.get(int(ex1.exit_status[0])), "xbest": [float(v) for v in ex1.xbest[0]],
+                "equal_to_pin": bool(int(ex1.num_iters[0]) == 25)}
+
     # ---------------------------------------------------------------- north_star's own target shape: 2^20 n=32 problems / GPU
     extra_1m = None
     if not args.skip_1m:
@@ -654,6 +662,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
+            "example1": example1,
             "bowl_1m": extra_1m,
             "profit_1m": extras.get("profit_1m"), "lmi64_diag": extras.get("lmi64_diag"), "lmi64_general": extras.get("lmi64_general"),
             "large_n": large,

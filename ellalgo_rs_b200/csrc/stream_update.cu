@@ -1027,6 +1027,7 @@ int ellcuda_dot_mv(ell_handle h, const double* x_dev, double* y_dev) {
 int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, double beta0, int32_t has_beta1, double beta1) {
     if (!h || !grad_dev) { set_error("null argument"); return ELLCUDA_E_ARG; }
     if (which < ELL_UPDATE_BIAS || which > ELL_UPDATE_Q) { set_error("bad update selector"); return ELLCUDA_E_ARG; }
+    NvtxRange nvtx_range("ellcuda_update_begin (sweep)");
     if (!h->parts.empty()) {   // group: the gradient is copied to every device (it must be complete when this is called), then
         for (ellcuda_ctx* p : h->parts) {   // every slab's sweep is enqueued before any finish can start waiting for peers
             ELL_DEVICE_SCOPE(p->device);
@@ -1055,6 +1056,7 @@ int ellcuda_update_begin(ell_handle h, int32_t which, const double* grad_dev, do
 
 int ellcuda_update_finish(ell_handle h) {
     if (!h) { set_error("null handle"); return ELLCUDA_E_ARG; }
+    NvtxRange nvtx_range("ellcuda_update_finish");
     if (!h->parts.empty()) {
         for (ellcuda_ctx* p : h->parts) { const int rc = ellcuda_update_finish(p); if (rc) return rc; }
         return ELLCUDA_OK;
@@ -1125,6 +1127,7 @@ int ellcuda_update(ell_handle h, int32_t which, const double* grad_host, double 
         return rc;
     }
     if (h->w != h->n) { set_error("ellcuda_update needs a whole-matrix handle; sharded handles use update_begin/finish"); return ELLCUDA_E_ARG; }
+    NvtxRange nvtx_range("ellcuda_update");
     ELL_DEVICE_SCOPE(h->device);
     ELL_CUDA_TRY(cudaMemcpyAsync(h->gstage, grad_host, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
     int rc = ellcuda_update_begin(h, which, h->gstage, beta0, has_beta1, beta1);
