@@ -99,6 +99,7 @@ __device__ int stable_update(const CalcConsts& cc, int which, const WarpMem& wm,
         // lane picks its two afterwards (selecting inside the loop cost 5 instructions per step instead of 1)
         const double oldt_init = oldt;
         __syncwarp();
+#pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const double temp = oldt + wm.sv[j];
             if (lane == 0) wm.sz[j] = temp;

@@ -160,6 +160,7 @@ __device__ bool lmi_assess(const LmiShared& L, const WarpMem& wm, int lane, doub
         if (lane >= i && lane < pos) wm.swit[lane] = wm.st[lane * m + (i - 1)] * wk;   // swit doubles as the product buffer here
         __syncwarp();
         double s = 0.0;
+#pragma unroll 4
         for (int k = i; k < pos; ++k) s += wm.swit[k];
         if (lane == i - 1) wk = -s;
         __syncwarp();
