@@ -427,6 +427,14 @@ int launch_k(const BatchArgs& a, cudaStream_t s, int sm_count, size_t fixed_byte
 
 }  // namespace
 
+// out[j][i] = in[i][j] for a rows x cols table (the lowpass spectrum for the kernels that read it from L2)
+int launch_transpose_table(const double* in, double* out, int rows, int cols, cudaStream_t s) {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    transpose_table_kernel<<<grid, block, 0, s>>>(in, out, rows, cols);
+    ELL_CUDA_TRY(cudaGetLastError());
+    return ELLCUDA_OK;
+}
+
 // Ell (KIND_ELL) with n <= 64: bowl / lowpass under cutting_plane_optim, the LMI oracles under cutting_plane_feas
 int launch_batch_ell64(const BatchArgs& a_in, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     BatchArgs a = a_in;
@@ -445,11 +453,12 @@ int launch_batch_ell64(const BatchArgs& a_in, int oracle_id, cudaStream_t s, int
         }
         double* tt = nullptr;   // the spectrum transposed: lanes evaluating consecutive rows then read consecutive addresses
         ELL_CUDA_TRY(cudaMallocAsync((void**)&tt, (size_t)a.aux[0] * a.n * 8, s));
-        dim3 grid((unsigned)((a.n + 31) / 32), (unsigned)((a.aux[0] + 31) / 32)), block(32, 8);
-        transpose_table_kernel<<<grid, block, 0, s>>>(a.table, tt, a.aux[0], a.n);
-        a.table_t = tt;
-        if (launches) *launches += 1;
-        rc = launch_k<OrLowpass64>(a, s, sm_count, 0, 0, kVec, 0);
+        rc = launch_transpose_table(a.table, tt, a.aux[0], a.n, s);
+        if (rc == ELLCUDA_OK) {
+            a.table_t = tt;
+            if (launches) *launches += 1;
+            rc = launch_k<OrLowpass64>(a, s, sm_count, 0, 0, kVec, 0);
+        }
         cudaFreeAsync(tt, s);
     } else if (oracle_id == ELL_ORACLE_LMI || oracle_id == ELL_ORACLE_LMI_OLD || oracle_id == ELL_ORACLE_LMI0) {
         const int lmi0 = oracle_id == ELL_ORACLE_LMI0;

@@ -418,7 +418,8 @@ int tuning_variant() {
 
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     if (a.n > 32 && a.n <= 64 && a.kind == ELL_KIND_ELL) return launch_batch_ell64(a, oracle_id, s, sm_count, launches);   // M in TMEM
-    if (a.n < 1 || a.n > 64) { set_error("the batched Ell kernels need 1 <= n <= 64"); return ELLCUDA_E_ARG; }
+    if (a.n > 64 && a.n <= 224 && a.kind == ELL_KIND_ELL) return launch_batch_ellcta(a, oracle_id, s, sm_count, launches);   // M in shared memory, one CTA
+    if (a.n < 1 || a.n > 224) { set_error("the batched Ell kernels need 1 <= n <= 224"); return ELLCUDA_E_ARG; }
     if (a.kind != ELL_KIND_ELL || a.mode != ELL_MODE_OPTIM) {
         set_error("warp-per-problem kernel: Ell + cutting_plane_optim only");
         return ELLCUDA_E_ARG;

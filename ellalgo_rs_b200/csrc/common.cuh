@@ -42,7 +42,7 @@ struct BatchArgs {
     double* xc;
     double* kappa;
     unsigned long long* queue;  // dynamic work counter (persistent kernels)
-    const double* table_t;      // launcher-made scratch: `table` transposed (batch_ell64.cu, lowpass with n > 32), else null
+    const double* table_t;      // launcher-made scratch: `table` transposed (batch_ell64.cu / batch_ellcta.cu, lowpass with n > 32), else null
 };
 
 // NVTX range for the scope of a host-side call (tracing); a no-op unless a profiler is attached
@@ -100,5 +100,7 @@ int launch_stable_single(double* qu_packed_upper, double* xc, double* scal_kappa
                          int use_parallel_cut, int which, const Cut& cut, cudaStream_t s);
 int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
 int launch_batch_ell64(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
+int launch_batch_ellcta(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches);
+int launch_transpose_table(const double* in, double* out, int rows, int cols, cudaStream_t s);
 
 }  // namespace ellcuda
