@@ -1,9 +1,10 @@
-// batch_ellcta.cu — batched cutting-plane loops on `Ell` (src/ell.rs) for 64 < n <= 224: ONE CTA PER PROBLEM, persistent,
+// batch_ellcta.cu — batched cutting-plane loops on `Ell` (src/ell.rs) for 32 < n <= 224: ONE CTA PER PROBLEM, persistent,
 // with the shape matrix M in SHARED MEMORY as a packed lower triangle.
 //
 // batch_warp.cu (n <= 32, rows in registers) and batch_ell64.cu (n <= 64, rows in tensor memory) give a problem to one
-// warp.  Above that a row no longer fits a lane pair, and the reference's own stress test runs LowpassOracle with 128 taps
-// (tests/stress_tests.rs:6-24), so here thread t of the CTA owns row t.  The reference computes the lower triangle of the
+// warp.  Above n = 64 a row no longer fits a lane pair, and the reference's own stress test runs LowpassOracle with 128 taps
+// (tests/stress_tests.rs:6-24), so here thread t of the CTA owns row t.  (It is also the faster kernel for most of
+// 32 < n <= 64 — see the routing in batch_warp.cu — which leaves the tensor-memory kernel the LMI oracles on `Ell`.)  The reference computes the lower triangle of the
 // rank-1 update and mirrors it (src/ell.rs:117-128), so after the first successful cut M is bitwise symmetric and only
 // P[i(i+1)/2 + j] = M[i][j], j <= i, is kept: 66 KB at n = 128 (3 resident CTAs per SM), 201 KB at n = 224, for all of
 // the problem's iterations — an update touches no HBM at all.  Row t of M.g reads P[T(t)+j] for j <= t and P[T(j)+t] above
@@ -370,7 +371,7 @@ int launch_k(const BatchArgs& a, cudaStream_t s, int sm_count) {
 
 }  // namespace
 
-// Ell (KIND_ELL) with 64 < n <= 224 under cutting_plane_optim: bowl / lowpass
+// Ell (KIND_ELL) with n <= 224 under cutting_plane_optim: bowl / lowpass
 int launch_batch_ellcta(const BatchArgs& a_in, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     BatchArgs a = a_in;
     if (a.kind != ELL_KIND_ELL || a.mode != ELL_MODE_OPTIM) {

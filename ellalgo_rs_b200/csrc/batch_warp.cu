@@ -417,8 +417,15 @@ int tuning_variant() {
 }  // namespace
 
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
+    // Above n = 32 the CTA-per-problem kernel (packed lower triangle in shared memory: half the rank-1 work, more problems
+    // resident) beats the warp-per-problem TMEM kernel — bowl n = 33 / 48 / 64: 351 / 280 / 211 against 217 / 190 / 143 M
+    // iterations/s; lowpass n = 48 / 56 / 64: 71 / 37 / 30 against 50 / 29 / 15, but n = 36 / 44: 95 / 52 against 110 / 72.
+    // ELLCUDA_CTA_MIN_N overrides the smallest n that goes to it (performance experiments; identical results).
+    int cta_min = ELL_ENV_INT("ELLCUDA_CTA_MIN_N", 0);
+    if (cta_min <= 0) cta_min = oracle_id == ELL_ORACLE_LOWPASS ? 48 : 33;
+    if (a.n > 32 && a.n >= cta_min && a.n <= 224 && a.kind == ELL_KIND_ELL && a.mode == ELL_MODE_OPTIM)
+        return launch_batch_ellcta(a, oracle_id, s, sm_count, launches);   // packed lower triangle of M in shared memory, one CTA
     if (a.n > 32 && a.n <= 64 && a.kind == ELL_KIND_ELL) return launch_batch_ell64(a, oracle_id, s, sm_count, launches);   // M in TMEM
-    if (a.n > 64 && a.n <= 224 && a.kind == ELL_KIND_ELL) return launch_batch_ellcta(a, oracle_id, s, sm_count, launches);   // M in shared memory, one CTA
     if (a.n < 1 || a.n > 224) { set_error("the batched Ell kernels need 1 <= n <= 224"); return ELLCUDA_E_ARG; }
     if (a.kind != ELL_KIND_ELL || a.mode != ELL_MODE_OPTIM) {
         set_error("warp-per-problem kernel: Ell + cutting_plane_optim only");

@@ -84,12 +84,17 @@ extern "C" {
                                      params[7] = p, A, k, a0, a1, v0, v1                    */
 #define ELL_ORACLE_PROFIT_RB    5 /* …:116-161  params[12] = the 7 above + e1..e5           */
 #define ELL_ORACLE_PROFIT_Q     6 /* …:163-198  optim_q, params[7]                          */
-#define ELL_ORACLE_LOWPASS      7 /* src/oracles/lowpass_oracle.rs:7-150  optim, n taps
+#define ELL_ORACLE_LOWPASS      7 /* src/oracles/lowpass_oracle.rs:7-150  optim, n taps, n <= 224
+                                     (tests/stress_tests.rs:6-14 uses 128)
                                      params[5] = wpass, wstop, lp_sq, up_sq, sp_sq
                                      table = spectrum, aux[0] = mdim rows × n (see
                                      ellcuda_lowpass_table)                                 */
-#define ELL_ORACLE_BOWL         8 /* tests/integration_test.rs:90-105 optim, any n
-                                     params[n] = target                                     */
+#define ELL_ORACLE_BOWL         8 /* tests/integration_test.rs:90-105 optim, n <= 224
+                                     params[n] = target.  Batched `Ell` keeps a problem's matrix
+                                     on the SM: one warp with the rows in registers (n <= 32) or
+                                     tensor memory (n <= 64), one CTA with the packed lower
+                                     triangle in shared memory (n <= 224); larger n: the
+                                     single-instance handle below                           */
 #define ELL_ORACLE_LMI          9 /* src/oracles/lmi_oracle.rs:5-45 + ldlt_mgr.rs  feas
                                      table = F_0..F_{n-1} (each m×m row-major) then B (m×m);
                                      aux[0] = m                                             */

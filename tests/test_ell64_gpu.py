@@ -1,7 +1,12 @@
-"""GPU parity tests of the batched `Ell` kernel for n <= 64 with M in tensor memory (csrc/batch_ell64.cu): the quadratic
-bowl and LowpassOracle for 32 < n <= 64 under cutting_plane_optim, and LMIOracle / LMIOldOracle / LMI0Oracle on the `Ell`
-space under cutting_plane_feas — the reference runs its LMI oracles under both search spaces
-(tests/lmi_tests.rs:174-225).  Bit for bit against the CPU checker."""
+"""GPU parity tests of batched `Ell` for 32 < n <= 64: the quadratic bowl and LowpassOracle under cutting_plane_optim
+(routed to the CTA-per-problem kernel csrc/batch_ellcta.cu, except lowpass below n = 48, and — in a child process with
+ELLCUDA_CTA_MIN_N=65 — through the tensor-memory kernel csrc/batch_ell64.cu), and LMIOracle / LMIOldOracle / LMI0Oracle on
+the `Ell` space under cutting_plane_feas with M in tensor memory — the reference runs its LMI oracles under both search
+spaces (tests/lmi_tests.rs:174-225).  Bit for bit against the CPU checker."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -116,3 +121,11 @@ def test_ell64_more_problems_than_resident_warps_and_empty(ref):
     g, r = both(ref, prob)
     assert_parity(g, r, exact=True, what="bowl n=64, 2 waves")
     assert batch.solve_batch(W.bowl(0, n=64)).num_iters.size == 0
+
+
+def test_tmem_kernel_bowl_and_lowpass_when_selected():
+    """the tensor-memory kernel's own bowl / lowpass paths (the default routing prefers the CTA kernel for them)"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, ELLCUDA_CTA_MIN_N="65")
+    out = subprocess.run([sys.executable, os.path.join(here, "ell64_tmem_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "tmem kernel ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
