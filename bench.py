@@ -14,7 +14,8 @@ by the sweep kernel itself (`--exchange nccl` selects an NCCL all_gather per upd
 reduce_mode 0 (bit-identical, the headline) AND the tolerance modes the sharded runs use (2, 4, 8), so that scaling can be
 read like for like; at every N it carries a `parity` record: the first two updates from M = I on this very configuration
 against the CPU checker (tsq, kappa, all of xc, rank 0's slab of M).  `profit_1m` (configs[1]) and `lmi64` (configs[3]) are
-timed the same way as the headline, each with its own CPU figure from the same box.
+timed the same way as the headline, each with its own CPU figure from the same box; `lowpass128` is LowpassOracle at the
+dimension of the reference's stress test (128 taps) as a batch.
 """
 from __future__ import annotations
 
@@ -598,6 +599,16 @@ def main():
                 st_, sm_ = (1, cnt_l) if general else (4, cnt_l // 4)     # C4b runs end after a few iterations: take them all
                 rec["cpu_baseline"] = cpu_leg(lambda k, hl=hl, st_=st_: strided(hl, st_, k), sm_, ni, es, st_)
             extras[name] = rec
+        # the reference's own stress dimension (tests/stress_tests.rs:6-14: LowpassOracle with 128 taps) as a batch: one CTA per
+        # problem, the packed lower triangle of M in shared memory (batch_ellcta.cu)
+        n_l, cnt_l = 128, 1776
+        hs = W.lowpass(cnt_l, batch.lowpass_table(n_l), n=n_l, first=rank * cnt_l, max_iters=3000)
+        rec, ni, es = timed_batch(hs, ("kappa0", "xc0", "gamma0", "params", "table"))
+        rec["workload"] = ("LowpassOracle with 128 taps (the dimension of tests/stress_tests.rs:6-14), Ell::new_with_scalar(40, 0), sane bounds, "
+                           "1776 instances per GPU, Options{max_iters 3000, tol 1e-14}")
+        if cpu_ok:
+            rec["cpu_baseline"] = cpu_leg(lambda k: strided(hs, 16, k), cnt_l // 16, ni, es, 16)
+        extras["lowpass128"] = rec
 
     # ---------------------------------------------------------------- CPU baseline of the headline (rank 0, N=1 only)
     cpu = None
@@ -665,6 +676,7 @@ def main():
             "example1": example1,
             "bowl_1m": extra_1m,
             "profit_1m": extras.get("profit_1m"), "lmi64_diag": extras.get("lmi64_diag"), "lmi64_general": extras.get("lmi64_general"),
+            "lowpass128": extras.get("lowpass128"),
             "large_n": large,
         }
         print(json.dumps(line), flush=True)

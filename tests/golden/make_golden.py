@@ -1,4 +1,4 @@
-"""Generates tests/golden/golden_v1.npz (round 1 cases; `--v1` to rewrite it) and golden_v2.npz (round 2 cases) with the CPU checker (oracle/).  The Rust reference cannot run in this image,
+"""Generates tests/golden/golden_v1.npz (round 1 cases; `--v1` to rewrite it) and golden_v2.npz / golden_v3.npz (round 2 cases) with the CPU checker (oracle/).  The Rust reference cannot run in this image,
 so these vectors are NOT reference output: they freeze the checker's results (which reproduce every count the
 reference's tests pin) so that a later change to oracle/ or to the kernels is caught against a committed artefact.
 Run from the repo root:  python tests/golden/make_golden.py"""
@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import ellref_py as R  # noqa: E402
-from golden_cases import CASES, CASES_V2, run_stepwise, run_stepwise_nonsym  # noqa: E402
+from golden_cases import CASES, CASES_V2, CASES_V3, run_stepwise, run_stepwise_nonsym  # noqa: E402
 
 FIELDS = ("xbest", "has_xbest", "num_iters", "exit_status", "gamma", "tsq", "xc", "kappa")
 out2 = {}
@@ -23,6 +23,13 @@ for k, v in st.items():
     out2[f"stepwise_nonsym/{k}"] = v
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_v2.npz"), **out2)
 print("wrote", len(out2), "arrays to golden_v2.npz")
+out3 = {}
+for name, make in CASES_V3.items():
+    o = R.solve(make(R))
+    for f in FIELDS:
+        out3[f"{name}/{f}"] = getattr(o, f)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_v3.npz"), **out3)
+print("wrote", len(out3), "arrays to golden_v3.npz")
 if "--v1" not in sys.argv:
     sys.exit(0)
 

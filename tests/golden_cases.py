@@ -88,3 +88,14 @@ def run_stepwise_nonsym(make_space, update, state):
         update(s, 0, W.large_n_grad(n, k), *W.LARGE_N_CUT)
     st = state(s)
     return {"xc": st["xc"], "mq": st["mq"], "kappa": np.array(st["kappa"]), "tsq": np.array(st["tsq"]), "mq_before_first_success": mid["mq"]}
+
+
+# ---------------------------------------------------------------------------------- round 2: tests/golden/golden_v3.npz
+# batched Ell above n = 64: one CTA per problem, packed lower triangle of M in shared memory (batch_ellcta.cu)
+CASES_V3 = {
+    "bowl128": lambda R: W.bowl(4, n=128, max_iters=2500),
+    "bowl100_nonsym": lambda R: _with(W.bowl(4, n=100, max_iters=500), mq0=_asym_batch(100, 4, 13, 100.0), kappa0=np.ones(1)),
+    "bowl224_no_defer": lambda R: _with(W.bowl(2, n=224, max_iters=300), no_defer_trick=True),
+    "lowpass128": lambda R: W.lowpass(3, R.lowpass_table(128), n=128, max_iters=2000),    # tests/stress_tests.rs:6-14's dimension
+    "lowpass72": lambda R: W.lowpass(3, R.lowpass_table(72), n=72, max_iters=2000),
+}

@@ -6,10 +6,11 @@ import numpy as np
 import pytest
 
 from ellalgo_rs_b200 import _abi as A
-from golden_cases import CASES, CASES_V2, run_stepwise, run_stepwise_nonsym
+from golden_cases import CASES, CASES_V2, CASES_V3, run_stepwise, run_stepwise_nonsym
 
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
 GOLD2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
+GOLD3 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v3.npz"))
 FIELDS = ("xbest", "has_xbest", "num_iters", "exit_status", "gamma", "tsq", "xc", "kappa")
 
 
@@ -85,3 +86,16 @@ def test_cuda_stepwise_nonsym_golden():
                              lambda s: dict(xc=s.xc(), mq=s.mq, kappa=s.kappa, tsq=s.tsq()))
     for k, v in st.items():
         assert np.array_equal(v, GOLD2[f"stepwise_nonsym/{k}"])
+
+
+# ---------------------------------------------------------------- batched Ell above n = 64 (golden_v3.npz)
+@pytest.mark.parametrize("name", list(CASES_V3))
+def test_checker_reproduces_golden_v3(ref, name):
+    _check(name, ref.solve(CASES_V3[name](ref)), GOLD3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES_V3))
+def test_cuda_reproduces_golden_v3(ref, name):
+    from ellalgo_rs_b200 import batch
+    _check(name, batch.solve_batch(CASES_V3[name](ref)), GOLD3)
