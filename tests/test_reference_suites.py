@@ -290,7 +290,7 @@ def test_quasicvx2_suite(ref, kind):
 @pytest.mark.parametrize("kind", SPACES)
 def test_stress_suite(ref, kind):
     """create_lowpass_case(n) is degenerate (lp_sq > up_sq): both runs must simply complete, as in the
-    reference; n = 128 goes through the large-n handle (the batched device oracle stops at n = 32)."""
+    reference; n = 128 goes through the large-n handle (host-driven here; the same case as a device batch is tests/test_ellcta_gpu.py::test_stress_lowpass_high_dimension_batched)."""
     params = ref.lowpass_case_params()
     x, niter, _ = solve(kind, ref, lambda: LowpassHost(ref, 128, params), 1.0, [0.0] * 128, float(params[4]),  # :6-14
                         Options(50000, 1e-14))
