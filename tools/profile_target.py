@@ -37,3 +37,8 @@ if what == "sym":        # symmetric storage, n = 16384: a few updates
 if what == "lmi":
     o = batch.solve_batch(W.lmi(1 << 15, n=64, m=16))
     print("lmi iterations", int(o.num_iters.sum()) + int((o.exit_status != 5).sum()))
+if what == "cta":        # one CTA per problem, packed triangle of M in shared memory: one wave of bowl and of lowpass at n = 128
+    o = batch.solve_batch(W.bowl(444, n=128, max_iters=500))
+    print("bowl128 iterations", int(o.num_iters.sum()) + int((o.exit_status != 5).sum()))
+    o = batch.solve_batch(W.lowpass(444, batch.lowpass_table(128), n=128, max_iters=300))
+    print("lowpass128 iterations", int(o.num_iters.sum()) + int((o.exit_status != 5).sum()))
