@@ -60,6 +60,42 @@ def test_fuzz_lowpass(ref, seed):  # lowpass32_tmem_kernel (n = 32) and batch_wa
     _check(ref, prob, f"lowpass fuzz seed={seed} n={n} count={count}")
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_cta_kernel(ref, seed):  # batch_ellcta_kernel: bowl n = 33..224, lowpass n = 48..224 (packed triangle in shared memory)
+    rng = np.random.default_rng(2500 + seed)
+    if seed < 4:
+        n = int(rng.integers(33, 225))
+        count = int(rng.integers(1, 30))
+        prob = W.bowl(count, n=n, max_iters=int(rng.integers(0, 500)), spread=float(rng.choice([0.3, 1.0, 3.0])))
+        prob.kappa0 = rng.uniform(1e-3, 1e3, count) if seed % 2 else np.full(count, float(rng.choice([1e-6, 1.0, 100.0, 1e8])))
+        prob.tolerance = float(rng.choice([1e-10, 1e-4, 1e3]))
+        if seed == 2:
+            prob.kappa0 = np.full(count, 1.0)
+            prob.diag0 = rng.uniform(0.5, 200.0, (count, n))
+        if seed == 3:
+            prob.kappa0 = np.full(count, 1.0)
+            prob.mq0 = np.ascontiguousarray(50.0 * (np.eye(n)[None] + rng.uniform(-1, 1, (count, n, n)) / (2 * n)))   # non-symmetric
+    else:
+        n = int(rng.integers(48, 225))
+        count = int(rng.integers(1, 8))
+        prob = W.lowpass(count, batch.lowpass_table(n), n=n, max_iters=int(rng.integers(1, 500)))
+        p = prob.params
+        p[:, 0] = rng.uniform(0.0, 0.6, count)
+        p[:, 1] = np.clip(p[:, 0] + rng.uniform(-0.05, 0.4, count), 0.0, 0.999)   # sometimes below wpass: empty transition band
+        dp = rng.uniform(0.005, 0.2, count)
+        p[:, 2] = (1.0 - dp) ** 2
+        p[:, 3] = (1.0 + dp) ** 2
+        if seed == 5:
+            p[::2, 2], p[::2, 3] = p[::2, 3].copy(), p[::2, 2].copy()              # lp_sq > up_sq
+        p[:, 4] = rng.uniform(1e-4, 0.5, count)
+        prob.gamma0 = p[:, 4].copy()
+        prob.kappa0 = rng.uniform(0.5, 200.0, count)
+        prob.tolerance = float(rng.choice([1e-14, 1e-6]))
+    prob.use_parallel_cut = bool(rng.integers(0, 2))
+    prob.no_defer_trick = bool(rng.integers(0, 2))
+    _check(ref, prob, f"cta fuzz seed={seed} n={n} count={count}")
+
+
 @pytest.mark.parametrize("seed", range(5))
 def test_fuzz_lmi_family(ref, seed):  # batch_stable_kernel: LMI / LMIOld / LMI0, diagonal and general starts
     rng = np.random.default_rng(3000 + seed)
