@@ -4,15 +4,17 @@
 // batch_warp.cu (n <= 32, rows in registers) and batch_ell64.cu (n <= 64, rows in tensor memory) give a problem to one
 // warp.  Above n = 64 a row no longer fits a lane pair, and the reference's own stress test runs LowpassOracle with 128 taps
 // (tests/stress_tests.rs:6-24), so here thread t of the CTA owns row t.  (It is also the faster kernel for most of
-// 32 < n <= 64 — see the routing in batch_warp.cu — which leaves the tensor-memory kernel the LMI oracles on `Ell`.)  The reference computes the lower triangle of the
-// rank-1 update and mirrors it (src/ell.rs:117-128), so after the first successful cut M is bitwise symmetric and only
-// P[i(i+1)/2 + j] = M[i][j], j <= i, is kept: 66 KB at n = 128 (3 resident CTAs per SM), 201 KB at n = 224, for all of
-// the problem's iterations — an update touches no HBM at all.  Row t of M.g reads P[T(t)+j] for j <= t and P[T(j)+t] above
-// the diagonal: the triangular numbers T(t) of 16 consecutive t are distinct mod 16, so both forms are free of bank
-// conflicts for 8-byte words.  A non-symmetric new_with_matrix start (src/ell.rs:31-41) is multiplied from the caller's
-// rows in global memory for the one product that can see it (iteration 0: a failed cut ends the loop, a successful one
-// mirrors the lower triangle).  The serial sums the whole CTA needs (omega, the bowl's f) and EllCalc run in warp 0 only
-// and are broadcast, which leaves the FP64 pipe to the other resident CTAs.
+// 32 < n <= 64 — see the routing in batch_warp.cu — which leaves the tensor-memory kernel the LMI oracles on `Ell`.)
+//
+// The reference computes the lower triangle of the rank-1 update and mirrors it (src/ell.rs:117-128), so after the first
+// successful cut M is bitwise symmetric and only P[i(i+1)/2 + j] = M[i][j], j <= i, is kept: 66 KB at n = 128 (3 resident
+// CTAs per SM), 201 KB at n = 224, for all of the problem's iterations — an update touches no HBM at all.  Row t of M.g
+// reads P[T(t)+j] for j <= t and P[T(j)+t] above the diagonal: the triangular numbers T(t) of 16 consecutive t are distinct
+// mod 16, so both forms are free of bank conflicts for 8-byte words.  A non-symmetric new_with_matrix start
+// (src/ell.rs:31-41) is multiplied from the caller's rows in global memory for the one product that can see it
+// (iteration 0: a failed cut ends the loop, a successful one mirrors the lower triangle).  The serial sums the whole CTA
+// needs (omega, the bowl's f) and EllCalc run in warp 0 only and are broadcast, which leaves the FP64 pipe to the other
+// resident CTAs.
 //
 //   cutting_plane_optim                  src/cutting_plane.rs:286-313
 //   Ell::update_core                     src/ell.rs:97-137 (grad_t, omega, xc, lower-triangle rank-1 + mirror, kappa)
