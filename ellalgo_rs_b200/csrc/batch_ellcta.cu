@@ -125,23 +125,43 @@ __device__ int cta_update(const Ctx& c, const CalcConsts& cc, int which, const C
     if (status != kSuccess) return status;
     xc -= c.sh->rho_over_omega * gt;
     c.srg[t] = c.sh->ratio * gt;
+    c.sp[t] = gt;                  // warp 0 has finished reading g .* grad_t: sp now carries grad_t for the rank-1 below
     kappa *= c.sh->delta;
     __syncthreads();
     const double scale = kappa;
     if (no_defer) kappa = 1.0;     // mq *= kappa; kappa = 1 (:132-135)
-    // element (i, j), j <= i: M[i][j] -= (ratio*grad_t[i]) * grad_t[j]; this thread holds column j = t
-    int ti = (c.warp * 32) * (c.warp * 32 + 1) / 2;
-    if (no_defer) {
-        for (int i = c.warp * 32; i < n; ++i) {
-            if (t <= i) c.P[ti + t] = (c.P[ti + t] - c.srg[i] * gt) * scale;
-            ti += i + 1;
-        }
-    } else {
+    // element (i, j), j <= i: M[i][j] -= (ratio*grad_t[i]) * grad_t[j].  Column chunk ch (columns 32ch .. 32ch+31) has rows
+    // 32ch .. n-1, so a warp that kept to its own columns would walk n rows in chunk 0 and n - 32ch in the others; the flat
+    // list of (chunk, row) warp-steps is dealt out in equal contiguous shares instead (grad_t of a foreign chunk: one load
+    // per chunk from sp, which holds grad_t since the barrier above).
+    int total = 0;
+    for (int ch = 0; ch < c.nwarps; ++ch) total += n - 32 * ch;
+    const int share = (total + c.nwarps - 1) / c.nwarps;
+    int f = c.warp * share;
+    const int fend = min(total, f + share);
+    int ch = 0, off = 0;
+    while (ch < c.nwarps && f >= off + (n - 32 * ch)) { off += n - 32 * ch; ++ch; }
+    while (f < fend) {
+        const int col = 32 * ch + c.lane;
+        const double gtc = c.sp[col];
+        int i = 32 * ch + (f - off);
+        const int iend = min(n, i + (fend - f));
+        int ti = i * (i + 1) / 2;
+        f += iend - i;
+        if (no_defer) {
+            for (; i < iend; ++i) {
+                if (col <= i) c.P[ti + col] = (c.P[ti + col] - c.srg[i] * gtc) * scale;
+                ti += i + 1;
+            }
+        } else {
 #pragma unroll 4
-        for (int i = c.warp * 32; i < n; ++i) {
-            if (t <= i) c.P[ti + t] -= c.srg[i] * gt;
-            ti += i + 1;
+            for (; i < iend; ++i) {
+                if (col <= i) c.P[ti + col] -= c.srg[i] * gtc;
+                ti += i + 1;
+            }
         }
+        off += n - 32 * ch;
+        ++ch;
     }
     return status;
 }

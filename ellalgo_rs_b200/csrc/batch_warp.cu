@@ -418,7 +418,7 @@ int tuning_variant() {
 
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     // Above n = 32 the CTA-per-problem kernel (packed lower triangle in shared memory: half the rank-1 work, more problems
-    // resident) beats the warp-per-problem TMEM kernel — bowl n = 33 / 48 / 64: 351 / 280 / 211 against 217 / 190 / 143 M
+    // resident) beats the warp-per-problem TMEM kernel — bowl n = 33 / 48 / 64: 389 / 285 / 218 against 217 / 190 / 143 M
     // iterations/s; lowpass n = 48 / 56 / 64: 71 / 37 / 30 against 50 / 29 / 15, but n = 36 / 44: 95 / 52 against 110 / 72.
     // ELLCUDA_CTA_MIN_N overrides the smallest n that goes to it (performance experiments; identical results).
     int cta_min = ELL_ENV_INT("ELLCUDA_CTA_MIN_N", 0);
