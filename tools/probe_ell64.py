@@ -1,4 +1,4 @@
-"""quick timings of the batched Ell n <= 64 kernel (M in TMEM): bowl n=48/64, LMI on Ell n=64 m=16, lowpass n=64"""
+"""quick timings of the batched Ell kernels for n <= 64: LMI on Ell n=64 m=16 and lowpass n=40 run in the TMEM kernel; bowl n=48/64 and lowpass n=64 go to the CTA kernel unless ELLCUDA_CTA_MIN_N=65"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
