@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "lmi_device.cuh"
+#include "stable_large_device.cuh"
 
 namespace ellcuda {
 namespace {
@@ -260,98 +261,14 @@ __global__ void __launch_bounds__(32) stable_single_kernel(double* __restrict__ 
 // subtracts its n-c-1 terms left to right starting with the most recently finished q[c+1] — a chain of n^2/2 dependent
 // subtractions by one thread (10 clocks each).  It exists so that EllStable drops in at any n the reference user may have;
 // the throughput path for EllStable is the batched kernel above.
-constexpr int kBigT = 1024;
-constexpr int kBigNMax = 2048;
-__device__ __forceinline__ long long upper_off_ll(long long r, long long n) { return r * n - r * (r - 1) / 2; }
+using namespace stable_large;
 
 __global__ void __launch_bounds__(kBigT) stable_large_kernel(double* __restrict__ qu, double* __restrict__ xc_g, double* __restrict__ scal,
                                                              int* __restrict__ status_out, const double* __restrict__ g, int n,
                                                              CalcConsts cc, int which, Cut cut) {
     extern __shared__ __align__(16) double sh[];
-    double* w = sh;               // inv(L) g
-    double* z = w + n;            // w .* d
-    double* q = z + n;            // mq * grad (back substitution)
-    double* gg = q + n;           // z .* w
-    double* t = gg + n;           // terms of the current back-substitution row; later beta2
-    double* oldt_a = t + n;       // oldt before adding gg[j]
-    double* temp_a = oldt_a + n;  // oldt + gg[j]
-    __shared__ double s_omega, s_roo, s_delta;
-    __shared__ int s_status;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += kBigT) w[i] = g[i];
-    // --- inv(L)*grad (:60-69): column j is applied once w[j] is final
-    for (int j = 0; j + 1 < n; ++j) {
-        __syncthreads();
-        const double wj = w[j];
-        const double* row = qu + upper_off_ll(j, n) - j;      // row[c] = Q[j][c], c >= j
-        for (int i = j + 1 + tid; i < n; i += kBigT) w[i] -= row[i] * wj;
-    }
-    __syncthreads();
-    // --- inv(D)*inv(L)*grad and omega (:72-83)
-    for (int i = tid; i < n; i += kBigT) {
-        const double d = qu[upper_off_ll(i, n)];
-        const double zi = w[i] * d;
-        z[i] = zi;
-        q[i] = zi;
-        gg[i] = zi * w[i];
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double acc = 0.0;
-        for (int k = 0; k < n; ++k) acc += gg[k];
-        const double tsq = scal[0] * acc;
-        Rsd r;
-        const int status = ell_calc(cc, which, cut, tsq, r);
-        scal[1] = tsq;                                        // tsq survives a failed cut (:85-90)
-        *status_out = status;
-        s_status = status;
-        s_omega = acc;
-        if (status == kSuccess) {
-            s_roo = r.rho / acc;
-            s_delta = r.delta;
-            const double mu = r.sigma / (1.0 - r.sigma);      // :107-108
-            double oldt = acc / mu;
-            for (int j = 0; j < n; ++j) {                     // temp = oldt + gg[j]; oldt = temp (:109-121)
-                const double temp = oldt + gg[j];
-                oldt_a[j] = oldt;
-                temp_a[j] = temp;
-                oldt = temp;
-            }
-        }
-    }
-    __syncthreads();
-    if (s_status != kSuccess) return;                         // state unchanged except tsq
-    // --- mq*grad = inv(L')*inv(D)*inv(L)*grad (:93-98): q[c] = z[c] - sum_{j>c, ascending} (Q[c][j]*w[c])*q[j]
-    for (int c = n - 2; c >= 0; --c) {
-        const double wc = w[c];
-        const double* row = qu + upper_off_ll(c, n) - c;
-        for (int j = c + 1 + tid; j < n; j += kBigT) t[j] = (row[j] * wc) * q[j];
-        __syncthreads();
-        if (tid == 0) {
-            double qc = q[c];
-            for (int j = c + 1; j < n; ++j) qc -= t[j];
-            q[c] = qc;
-        }
-        __syncthreads();
-    }
-    // --- xc (:101-104), beta2 and the new diagonal (:110-120)
-    const double roo = s_roo;
-    for (int i = tid; i < n; i += kBigT) {
-        xc_g[i] -= roo * q[i];
-        t[i] = z[i] / temp_a[i];                              // beta2 = inv_md_inv_ml_g[j] / temp
-    }
-    __syncthreads();
-    // --- rank-one update of the factor: mq[j][l] += beta2 * mq[l][j], l > j, with the scratch entry mq[l][j] = Q[j][l]*w[j]
-    for (int j = 0; j < n; ++j) {
-        double* row = qu + upper_off_ll(j, n) - j;
-        const double bj = t[j], wj = w[j];
-        for (int l = j + 1 + tid; l < n; l += kBigT) {
-            const double v = row[l];
-            row[l] = v + bj * (v * wj);
-        }
-        if (tid == 0) row[j] = row[j] * (oldt_a[j] / temp_a[j]);   // mq[j][j] *= oldt / temp
-    }
-    if (tid == 0) scal[0] = scal[0] * s_delta;                // kappa *= delta (:122)
+    __shared__ StableLargeShared ss;
+    stable_large_body(qu, xc_g, scal, status_out, g, n, cc, which, cut, sh, ss, (int)threadIdx.x);
 }
 
 }  // namespace

@@ -7,68 +7,7 @@
 //     with a barrier is reported by ThreadSanitizer as a data race (SURVEY.md §5 "race detection"; compute-sanitizer's
 //     racecheck is closed on the GPU pool).
 // Test infrastructure only: nothing in the product links this.
-#include <pthread.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdint>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <thread>
-#include <vector>
-
-// ---------------------------------------------------------------------------------------------- CUDA built-ins, emulated
-namespace emu {
-struct Cta {
-    pthread_barrier_t all;
-    std::vector<pthread_barrier_t> warp;
-    std::vector<uint64_t> slot;    // 32 exchange slots per warp
-};
-thread_local Cta* cta = nullptr;
-thread_local int tid = 0;
-inline void warp_barrier() { pthread_barrier_wait(&cta->warp[tid >> 5]); }
-inline uint64_t* slots() { return cta->slot.data() + 32 * (tid >> 5); }
-}  // namespace emu
-
-// EMU_DROP_BARRIER=<k> (self-test of the race detector): every thread skips its k-th __syncthreads, which keeps the
-// barrier counts consistent but removes one ordering — ThreadSanitizer must then report a race
-static const long emu_drop = std::getenv("EMU_DROP_BARRIER") ? std::atol(std::getenv("EMU_DROP_BARRIER")) : -1;
-static thread_local long emu_barriers = 0;
-static inline void __syncthreads() {
-    if (emu_barriers++ == emu_drop) return;
-    pthread_barrier_wait(&emu::cta->all);
-}
-static inline unsigned __ballot_sync(unsigned, int pred) {
-    uint64_t* s = emu::slots();
-    s[emu::tid & 31] = pred ? 1 : 0;
-    emu::warp_barrier();
-    unsigned m = 0;
-    for (int l = 0; l < 32; ++l) m |= (unsigned)s[l] << l;
-    emu::warp_barrier();
-    return m;
-}
-template <class T>
-static inline T __shfl_xor_sync(unsigned, T v, int off) {
-    static_assert(sizeof(T) <= 8, "");
-    uint64_t* s = emu::slots();
-    uint64_t bits = 0;
-    std::memcpy(&bits, &v, sizeof(T));
-    s[emu::tid & 31] = bits;
-    emu::warp_barrier();
-    bits = s[(emu::tid & 31) ^ off];
-    emu::warp_barrier();
-    T out;
-    std::memcpy(&out, &bits, sizeof(T));
-    return out;
-}
-static inline double __ldg(const double* p) { return *p; }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
-    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
-}
-static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
-using std::min;
+#include "cuda_emu.h"
 
 #include "../../ellalgo_rs_b200/csrc/ellcta_device.cuh"
 
@@ -86,24 +25,10 @@ static void run_grid(const BatchArgs& a, int ctas) {
     std::vector<std::thread> grid;
     for (int b = 0; b < ctas; ++b)
         grid.emplace_back([&a, nt, doubles] {
-            emu::Cta cta;
-            pthread_barrier_init(&cta.all, nullptr, nt);
-            cta.warp.resize(nt / 32);
-            for (auto& w : cta.warp) pthread_barrier_init(&w, nullptr, 32);
-            cta.slot.assign(nt, 0);
             std::vector<double> smem(doubles, NAN);    // uninitialised shared memory must never reach a result
             CtaShared sh;
             std::memset(&sh, 0xff, sizeof sh);
-            std::vector<std::thread> ts;
-            for (int t = 0; t < nt; ++t)
-                ts.emplace_back([&, t] {
-                    emu::cta = &cta;
-                    emu::tid = t;
-                    ellcta_body<Oracle>(a, smem.data(), sh, t, nt);
-                });
-            for (auto& t : ts) t.join();
-            pthread_barrier_destroy(&cta.all);
-            for (auto& w : cta.warp) pthread_barrier_destroy(&w);
+            emu::run_cta(nt, [&](int t) { ellcta_body<Oracle>(a, smem.data(), sh, t, nt); });
         });
     for (auto& g : grid) g.join();
 }
