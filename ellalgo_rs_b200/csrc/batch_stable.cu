@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(kBigT) stable_large_kernel(double* __restrict_
 
 }  // namespace
 
+#ifdef __CUDACC__   // host launchers: left out when tests/cpp/emu_lmi.cpp compiles the kernels above for the host
 int launch_stable_single(double* qu, double* xc, double* scal, int* status, const double* g, int n, int use_parallel_cut, int which,
                          const Cut& cut, cudaStream_t s) {
     const CalcConsts cc = CalcConsts::make(n, use_parallel_cut);
@@ -345,5 +346,7 @@ int launch_batch_stable(const BatchArgs& a, int oracle_id, cudaStream_t s, int s
     if (launches) *launches += 1;
     return ELLCUDA_OK;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace ellcuda

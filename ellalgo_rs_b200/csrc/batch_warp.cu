@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_warp_kernel(const Batc
     }
 }
 
+#ifdef __CUDACC__   // host launchers: left out when tests/cpp/emu_batch_warp.cpp compiles the kernels above for the host
 template <class Oracle, bool FIXED32, int WARPS, int MINB>
 int launch_one(const BatchArgs& a, cudaStream_t s, int sm_count) {
     const int n = a.n;
@@ -414,8 +415,11 @@ int tuning_variant() {
     return ELL_ENV_INT("ELLCUDA_TUNE", 0);   // read once per process
 }
 
+#endif  // __CUDACC__
+
 }  // namespace
 
+#ifdef __CUDACC__
 int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     // Above n = 32 the CTA-per-problem kernel (packed lower triangle in shared memory: half the rank-1 work, more problems
     // resident) beats the warp-per-problem TMEM kernel — bowl n = 33 / 48 / 64: 389 / 285 / 218 against 217 / 190 / 143 M
@@ -465,5 +469,7 @@ int launch_batch_warp(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_
     if (rc == ELLCUDA_OK && launches) *launches += 1;
     return rc;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace ellcuda

@@ -1,8 +1,10 @@
-// cuda_emu.h — the few CUDA built-ins the CTA-wide kernels use, emulated on the host: one OS thread per CUDA thread of a
-// CTA, a pthread barrier for __syncthreads, per-warp barriers behind __ballot_sync / __shfl_xor_sync.  Include it BEFORE
-// the device header under test.  Test infrastructure (tests/cpp/emu_*.cpp); see tests/test_ellcta_emulated.py.
+// cuda_emu.h — the few CUDA built-ins the CTA- and warp-wide kernels use, emulated on the host: one OS thread per CUDA thread
+// of a CTA, a pthread barrier for __syncthreads, per-warp pthread barriers for __syncwarp, and a rendezvous the sanitizer
+// cannot see behind __ballot_sync / __shfl*_sync.  Include it BEFORE the device code under test.
+// Test infrastructure (tests/cpp/emu_*.cpp); see tests/test_emulated_kernels.py.
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cmath>
@@ -19,26 +21,66 @@ namespace emu {
 // that is already waiting in round k+1 would "publish" its accesses to a thread still leaving round k and hide a race
 // between them.  Rotating over four barrier objects keeps the rounds apart (also across one deliberately skipped round).
 constexpr int kRot = 4;
+
+// Shuffles and ballots exchange registers and order NO memory on the device.  Their emulation needs a rendezvous, but it must
+// not hand ThreadSanitizer a happens-before edge (a missing __syncwarp next to a shuffle would hide behind it), so it is a
+// sense-reversing barrier on plain atomics inside functions the sanitizer does not instrument.
+#define EMU_QUIET __attribute__((no_sanitize("thread"), noinline))
+struct QuietBarrier {
+    unsigned count = 0, sense = 0;
+};
+
 struct Cta {
     pthread_barrier_t all[kRot];
     std::vector<pthread_barrier_t> warp;   // kRot per warp
+    std::vector<QuietBarrier> quiet;       // one per warp
     std::vector<uint64_t> slot;            // 32 exchange slots per warp
 };
 thread_local Cta* cta = nullptr;
 thread_local int tid = 0;
 thread_local long warp_rounds = 0;
+thread_local unsigned quiet_sense = 0;
+
 inline void warp_barrier() { pthread_barrier_wait(&cta->warp[(size_t)kRot * (tid >> 5) + (warp_rounds++ & (kRot - 1))]); }
-inline uint64_t* slots() { return cta->slot.data() + 32 * (tid >> 5); }
+
+EMU_QUIET inline void quiet_wait() {
+    QuietBarrier* b = &cta->quiet[tid >> 5];
+    const unsigned my = quiet_sense ^= 1u;
+    if (__atomic_add_fetch(&b->count, 1u, __ATOMIC_ACQ_REL) == 32u) {
+        __atomic_store_n(&b->count, 0u, __ATOMIC_RELAXED);
+        __atomic_store_n(&b->sense, my, __ATOMIC_RELEASE);
+    } else {
+        for (unsigned spins = 0; __atomic_load_n(&b->sense, __ATOMIC_ACQUIRE) != my; ++spins)
+            if (spins > 32) sched_yield();
+    }
+}
+// every lane deposits 8 bytes, then reads the deposit of lane `src` (or all 32, for a ballot)
+EMU_QUIET inline uint64_t exchange(uint64_t mine, int src) {
+    uint64_t* s = cta->slot.data() + 32 * (tid >> 5);
+    s[tid & 31] = mine;
+    quiet_wait();
+    const uint64_t got = s[src & 31];
+    quiet_wait();
+    return got;
+}
+EMU_QUIET inline unsigned gather_bits(bool mine) {
+    uint64_t* s = cta->slot.data() + 32 * (tid >> 5);
+    s[tid & 31] = mine ? 1 : 0;
+    quiet_wait();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (unsigned)s[l] << l;
+    quiet_wait();
+    return m;
+}
 }  // namespace emu
 
-// EMU_DROP_BARRIER=<k> (self-test of the race detector): every thread skips its k-th __syncthreads, which keeps the
-// barrier counts consistent but removes one ordering — ThreadSanitizer must then report a race
+// EMU_DROP_BARRIER=<k> / EMU_DROP_SYNCWARP=<k> (self-test of the race detector): every thread skips its k-th __syncthreads /
+// __syncwarp, which keeps the barrier counts consistent but removes one ordering — ThreadSanitizer must then report a race
 static const long emu_drop = std::getenv("EMU_DROP_BARRIER") ? std::atol(std::getenv("EMU_DROP_BARRIER")) : -1;
-static thread_local long emu_barriers = 0;
-static inline void __syncthreads() {
-    const long k = emu_barriers++;
-    if (k == emu_drop) return;
-    pthread_barrier_wait(&emu::cta->all[k & (emu::kRot - 1)]);
+static const long emu_drop_warp = std::getenv("EMU_DROP_SYNCWARP") ? std::atol(std::getenv("EMU_DROP_SYNCWARP")) : -1;
+static thread_local long emu_barriers = 0, emu_syncwarps = 0;
+
+static inline void emu_jitter(long k) {
 #ifdef EMU_JITTER
     // a pseudo-random quarter of the threads leaves each barrier a little late: accesses that only a barrier orders are then
     // rarely simultaneous to the instruction, which is where ThreadSanitizer's shadow can miss them
@@ -46,31 +88,50 @@ static inline void __syncthreads() {
         volatile int spin = 0;
         for (int i = 0; i < 400; ++i) spin = spin + i;
     }
+#else
+    (void)k;
 #endif
 }
-static inline unsigned __ballot_sync(unsigned, int pred) {
-    uint64_t* s = emu::slots();
-    s[emu::tid & 31] = pred ? 1 : 0;
-    emu::warp_barrier();
-    unsigned m = 0;
-    for (int l = 0; l < 32; ++l) m |= (unsigned)s[l] << l;
-    emu::warp_barrier();
-    return m;
+static inline void emu_syncthreads_at(const char* file, int line) {
+    const long k = emu_barriers++;
+    if (k == emu_drop) {
+        if (emu::tid == 0) std::fprintf(stderr, "[emu] dropped the __syncthreads at %s:%d\n", file, line);
+        return;
+    }
+    pthread_barrier_wait(&emu::cta->all[k & (emu::kRot - 1)]);
+    emu_jitter(k);
 }
+static inline void emu_syncwarp_at(const char* file, int line) {
+    const long k = emu_syncwarps++;
+    if (k == emu_drop_warp) {
+        if (emu::tid == 0) std::fprintf(stderr, "[emu] dropped the __syncwarp at %s:%d\n", file, line);
+        return;
+    }
+    emu::warp_barrier();
+    emu_jitter(k + 7);
+}
+#define __syncthreads() emu_syncthreads_at(__FILE__, __LINE__)
+#define __syncwarp(...) emu_syncwarp_at(__FILE__, __LINE__)
+
+static inline unsigned __ballot_sync(unsigned, int pred) { return emu::gather_bits(pred != 0); }
 template <class T>
-static inline T __shfl_xor_sync(unsigned, T v, int off) {
+static inline T __shfl_sync(unsigned, T v, int src) {
     static_assert(sizeof(T) <= 8, "");
-    uint64_t* s = emu::slots();
     uint64_t bits = 0;
     std::memcpy(&bits, &v, sizeof(T));
-    s[emu::tid & 31] = bits;
-    emu::warp_barrier();
-    bits = s[(emu::tid & 31) ^ off];
-    emu::warp_barrier();
+    bits = emu::exchange(bits, src);
     T out;
     std::memcpy(&out, &bits, sizeof(T));
     return out;
 }
+template <class T>
+static inline T __shfl_xor_sync(unsigned m, T v, int off) { return __shfl_sync(m, v, (emu::tid & 31) ^ off); }
+
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
+static thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 static inline double __ldg(const double* p) { return *p; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
@@ -78,22 +139,27 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 using std::min;
 
-
 namespace emu {
 // runs fn(tid) on nt concurrent OS threads that form one emulated CTA
 template <class F>
 inline void run_cta(int nt, F fn) {
     Cta c;
+    const size_t warps = (size_t)(nt + 31) / 32;
     for (auto& b : c.all) pthread_barrier_init(&b, nullptr, nt);
-    c.warp.resize((size_t)kRot * ((nt + 31) / 32));
+    c.warp.resize(kRot * warps);
     for (auto& w : c.warp) pthread_barrier_init(&w, nullptr, 32);
-    c.slot.assign((size_t)32 * ((nt + 31) / 32), 0);
+    c.quiet.resize(warps);
+    c.slot.assign(32 * warps, 0);
     std::vector<std::thread> ts;
     for (int t = 0; t < nt; ++t)
-        ts.emplace_back([&c, &fn, t] {
+        ts.emplace_back([&c, &fn, t, nt] {
             cta = &c;
             tid = t;
             warp_rounds = 0;
+            quiet_sense = 0;
+            threadIdx.x = (unsigned)t; threadIdx.y = threadIdx.z = 0;
+            blockIdx.x = blockIdx.y = blockIdx.z = 0;
+            blockDim.x = (unsigned)nt;
             fn(t);
         });
     for (auto& t : ts) t.join();

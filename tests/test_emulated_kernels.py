@@ -28,16 +28,21 @@ BUILD = os.path.join(CPP, "_build")
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
 SRC = os.path.join(CPP, "emu_ellcta.cpp")
 SRC_ST = os.path.join(CPP, "emu_stable_large.cpp")
+SRC_BW = os.path.join(CPP, "emu_batch_warp.cpp")
+SRC_LMI = os.path.join(CPP, "emu_lmi.cpp")
+LIB_LMI, TSAN_LMI = os.path.join(BUILD, "libemu_lmi.so"), os.path.join(BUILD, "emu_lmi_tsan")
+LIB_BW, TSAN_BW = os.path.join(BUILD, "libemu_batch_warp.so"), os.path.join(BUILD, "emu_batch_warp_tsan")
 LIB, TSAN = os.path.join(BUILD, "libemu_ellcta.so"), os.path.join(BUILD, "emu_ellcta_tsan")
 LIB_ST, TSAN_ST = os.path.join(BUILD, "libemu_stable_large.so"), os.path.join(BUILD, "emu_stable_large_tsan")
-DEPS = [os.path.join(CPP, "cuda_emu.h")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "common.cuh",
+DEPS = [os.path.join(CPP, "cuda_emu.h")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "batch_warp.cu",
+                                                                              "batch_stable.cu", "lmi_device.cuh", "common.cuh",
                                                                               "ell_calc.cuh")]
 
 
 def _build(out, extra, src=SRC):
     os.makedirs(BUILD, exist_ok=True)
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS + [src]):
-        subprocess.run(["g++", "-std=c++17", "-g", "-ffp-contract=off", "-Wno-attributes", "-I", CUDA_INC, src] + extra +
+        subprocess.run(["g++", "-std=c++17", "-g", "-ffp-contract=off", "-Wno-attributes", "-Wno-unknown-pragmas", "-I", CUDA_INC, src] + extra +
                        ["-o", out, "-lpthread", "-ldl"], check=True, capture_output=True, text=True)
     return out
 
@@ -93,10 +98,10 @@ def _tsan_exe():
     return _build(TSAN, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER"])
 
 
-def _races_with_dropped_barrier(exe, k):
-    """every emulated thread skips its k-th __syncthreads; returns whether ThreadSanitizer reported a data race"""
+def _races_with_dropped_barrier(exe, k, var="EMU_DROP_BARRIER"):
+    """every emulated thread skips its k-th __syncthreads (or __syncwarp); returns whether ThreadSanitizer reported a data race"""
     try:
-        p = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, EMU_DROP_BARRIER=str(k)))
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, **{var: str(k)}))
         err = p.stderr
     except subprocess.TimeoutExpired as e:            # without the barrier the threads may also diverge and hang
         err = (e.stderr or b"").decode() if isinstance(e.stderr, bytes) else (e.stderr or "")
@@ -159,3 +164,90 @@ def test_ellstable_update_no_data_race_under_thread_sanitizer():
     assert "step 2: status 1" in p.stdout and "step 3: status 0" in p.stdout
     assert _races_with_dropped_barrier(exe, 5)            # forward substitution: w[j] final before column j is applied
     assert _races_with_dropped_barrier(exe, 150)          # back substitution: the row's terms before thread 0 sums them
+
+
+# ------------------------------------------------------------------------------------------ warp-per-problem kernels, n <= 32
+@pytest.fixture(scope="module")
+def emu_warp():
+    lib = C.CDLL(_build(LIB_BW, ["-O2", "-fPIC", "-shared"], SRC_BW))
+    lib.emu_batch_warp_solve.restype = C.c_int
+    lib.emu_batch_warp_solve.argtypes = [C.c_void_p, C.c_void_p]
+
+    def solve(prob):
+        out = BatchOutput.empty(prob.count, prob.n)
+        d, r = prob.to_desc(0), out.to_result()
+        assert lib.emu_batch_warp_solve(C.byref(d), C.byref(r)) == 0
+        return out
+    return solve
+
+
+def test_emulated_warp_kernels_equal_checker(ref, emu_warp):  # csrc/batch_warp.cu compiled for the host
+    rng = np.random.default_rng(11)
+    for n, count, iters in ((7, 5, 200), (20, 5, 150), (32, 6, 150)):          # generic and FIXED32 variants
+        prob = W.bowl(count, n=n, max_iters=iters)
+        assert_parity(emu_warp(prob), ref.solve(prob), exact=True, what=f"emulated warp bowl n={n}")
+        prob.kappa0 = np.ones(1)
+        prob.mq0 = np.ascontiguousarray(100.0 * (np.eye(n)[None] + rng.uniform(-1, 1, (count, n, n)) / n))   # non-symmetric start
+        prob.no_defer_trick = True
+        assert_parity(emu_warp(prob), ref.solve(prob), exact=True, what=f"emulated warp bowl n={n} matrix start")
+    for n, count, iters in ((12, 3, 400), (31, 2, 300)):
+        prob = W.lowpass(count, ref.lowpass_table(n), n=n, max_iters=iters)
+        assert_parity(emu_warp(prob), ref.solve(prob), exact=True, what=f"emulated warp lowpass n={n}")
+    n = 32                                               # n = 32 from a matrix start: the variant the TMEM kernel leaves to this file
+    prob = W.lowpass(2, ref.lowpass_table(n), n=n, max_iters=500)
+    a = rng.uniform(-1, 1, (n, n)) / (4 * n)
+    prob.mq0 = np.ascontiguousarray(np.eye(n) + a + a.T)
+    assert_parity(emu_warp(prob), ref.solve(prob), exact=True, what="emulated warp lowpass n=32 matrix start")
+
+
+def test_warp_kernels_no_data_race_under_thread_sanitizer():
+    """lanes exchange vectors through shared memory ordered only by __syncwarp (a per-warp barrier here): none may be missing"""
+    exe = _build(TSAN_BW, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER"], SRC_BW)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "lowpass n=32: rc 0" in p.stdout and "3 of 3 with xbest" in p.stdout
+    # sensitivity: each of the first twelve __syncwarp calls was dropped once by hand, every drop was reported; two re-checked here
+    assert _races_with_dropped_barrier(exe, 1, "EMU_DROP_SYNCWARP")       # the oracle's, before the ordered sum of f
+    assert _races_with_dropped_barrier(exe, 4, "EMU_DROP_SYNCWARP")       # update_core's last, before the rank-1 reads ratio*grad_t
+
+
+# ------------------------------------------------------------------------------------------ EllStable + LMI (configs[3])
+def test_emulated_lmi_kernel_equals_checker(ref):  # csrc/batch_stable.cu + lmi_device.cuh compiled for the host
+    from ellalgo_rs_b200 import _abi as A
+    lib = C.CDLL(_build(LIB_LMI, ["-O2", "-fPIC", "-shared"], SRC_LMI))
+    lib.emu_lmi_solve.restype = C.c_int
+    lib.emu_lmi_solve.argtypes = [C.c_void_p, C.c_void_p]
+
+    def solve(prob):
+        out = BatchOutput.empty(prob.count, prob.n)
+        d, r = prob.to_desc(0), out.to_result()
+        assert lib.emu_lmi_solve(C.byref(d), C.byref(r)) == 0
+        return out
+    for n, m, count in ((64, 16, 3), (20, 7, 4), (33, 17, 2)):          # m <= 16: two LDL^T rows per step; m = 17: one row per step
+        prob = W.lmi(count, n=n, m=m)
+        prob.max_iters = 150
+        g, r = solve(prob), ref.solve(prob)
+        assert_parity(g, r, exact=True, what=f"emulated LMI n={n} m={m}")
+        prob.oracle_id = A.ORACLE_LMI_OLD
+        assert_parity(solve(prob), ref.solve(prob), exact=True, what=f"emulated LMIOld n={n} m={m}")
+    assert g.num_iters.max() > 3
+    prob = W.lmi(3, n=40, m=9, general=True, upper_scale=1e-6)          # EllStable::new_with_matrix: the GENERAL factor variant
+    prob.max_iters = 60
+    assert_parity(solve(prob), ref.solve(prob), exact=True, what="emulated LMI general start")
+    prob = W.lmi0(4, n=24, m=8)
+    prob.max_iters = 200
+    g, r = solve(prob), ref.solve(prob)
+    assert_parity(g, r, exact=True, what="emulated LMI0")
+    assert (g.exit_status == A.EXIT_FEASIBLE).any()
+
+
+def test_lmi_kernel_no_data_race_under_thread_sanitizer():
+    """24 __syncwarp per iteration order the factor rows, the witness and the EllStable vectors between lanes"""
+    exe = _build(TSAN_LMI, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER"], SRC_LMI)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "LMI0 diagonal start: rc 0" in p.stdout and "4 of 4 feasible" in p.stdout
+    # sensitivity: the first 48 __syncwarp calls were each dropped once by hand and 47 drops were reported (the 48th, the pair
+    # loop's closing __syncwarp in its first round, is covered by the next step's); two re-checked here
+    assert _races_with_dropped_barrier(exe, 2, "EMU_DROP_SYNCWARP")
+    assert _races_with_dropped_barrier(exe, 22, "EMU_DROP_SYNCWARP")      # the two-rows-per-step LDL^T: end of a step
