@@ -22,7 +22,10 @@
 namespace ellcuda {
 namespace {
 
-constexpr int kWarps = 8;            // 8 problems per SM: 4 lane quarters x 2 column halves
+#ifndef ELLCUDA_ELL64_WARPS
+#define ELLCUDA_ELL64_WARPS 8        // the host emulation under ThreadSanitizer builds with 6 (it tracks <= 256 running threads)
+#endif
+constexpr int kWarps = ELLCUDA_ELL64_WARPS;   // 8 problems per SM: 4 lane quarters x 2 column halves
 constexpr int kColsPerProblem = 256; // 2 rows x 64 doubles x 2 columns
 constexpr int kVec = 5 * kNMax;      // per-warp vectors: sx | sg | sgt | srg | sp
 
@@ -396,6 +399,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) batch_ell64_kernel(const Batch
     tm_free_all(tm_base, warp);
 }
 
+#ifdef __CUDACC__   // host launchers (and the transpose they launch): left out when tests/cpp/emu_ell64.cpp compiles the kernel above for the host
 __global__ void transpose_table_kernel(const double* __restrict__ in, double* __restrict__ out, int rows, int cols) {
     __shared__ double t[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
@@ -425,8 +429,11 @@ int launch_k(const BatchArgs& a, cudaStream_t s, int sm_count, size_t fixed_byte
     return ELLCUDA_OK;
 }
 
+#endif  // __CUDACC__
+
 }  // namespace
 
+#ifdef __CUDACC__
 // out[j][i] = in[i][j] for a rows x cols table (the lowpass spectrum for the kernels that read it from L2)
 int launch_transpose_table(const double* in, double* out, int rows, int cols, cudaStream_t s) {
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
@@ -481,5 +488,7 @@ int launch_batch_ell64(const BatchArgs& a_in, int oracle_id, cudaStream_t s, int
     if (rc == ELLCUDA_OK && launches) *launches += 1;
     return rc;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace ellcuda

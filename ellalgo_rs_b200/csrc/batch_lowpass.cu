@@ -227,13 +227,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
         const int r = idx >> 5, col = idx & 31;
         smem[r * kTabStride + col] = a.table[idx];
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n"
-                     :: "l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    tm_fence_sync();
-    const uint32_t tm_base = tmem_base_s;
+    const uint32_t tm_base = tm_alloc_all(&tmem_base_s, warp);   // all 512 columns; the barrier inside also publishes the table
     const uint32_t tm_lane = tm_base + ((uint32_t)(32 * (warp & 3)) << 16);
     if (kTabTm > 0 && warp < 4) {   // one warp per lane quarter stores the tail columns of row 32*b + lane in column block b
         for (int b = 0; b < rows / 32; ++b) {
@@ -353,11 +347,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) lowpass32_tmem_kernel(const Ba
         __syncwarp();
     }
 
-    tm_fence_sync();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tm_base) : "memory");
+    tm_free_all(tm_base, warp);
 }
 
+#ifdef __CUDACC__   // host launchers: left out when tests/cpp/emu_lowpass32.cpp compiles the kernel above for the host
 template <int kTabTm, bool kAligned, int kWarps>
 int launch_variant(const BatchArgs& a, cudaStream_t s, int sm_count) {
     const size_t tab = ((size_t)a.aux[0] * kTabStride + 1) & ~(size_t)1;
@@ -373,8 +366,11 @@ int launch_variant(const BatchArgs& a, cudaStream_t s, int sm_count) {
     return ELLCUDA_OK;
 }
 
+#endif  // __CUDACC__
+
 }  // namespace
 
+#ifdef __CUDACC__
 int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, long long* launches) {
     if (a.n != kN || a.aux[0] != 15 * kN) { set_error("lowpass32 kernel needs n = 32 and a 480-row spectrum"); return ELLCUDA_E_ARG; }
     if (a.mq0) { set_error("lowpass32 kernel: diagonal starts only"); return ELLCUDA_E_ARG; }
@@ -390,5 +386,7 @@ int launch_batch_lowpass32(const BatchArgs& a, cudaStream_t s, int sm_count, lon
     if (rc == ELLCUDA_OK && launches) *launches += 1;
     return rc;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace ellcuda

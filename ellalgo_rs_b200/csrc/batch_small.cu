@@ -691,6 +691,7 @@ __global__ void __launch_bounds__(128) batch_small_kernel(const BatchArgs a) {
     }
 }
 
+#ifdef __CUDACC__   // the launch itself: tests/cpp/emu_batch_small.cpp supplies a host emulation of launch_kind under the same dispatch table
 template <class Oracle, int MODE>
 int launch_kind(const BatchArgs& a, cudaStream_t s, int sm_count) {
     const long long warps_needed = (a.count + 31) / 32;
@@ -707,8 +708,11 @@ int launch_kind(const BatchArgs& a, cudaStream_t s, int sm_count) {
     return ELLCUDA_OK;
 }
 
+#endif  // __CUDACC__
+
 }  // namespace
 
+#ifdef __CUDACC__
 __global__ void math_probe_kernel(int which, const double* __restrict__ x, double* __restrict__ y, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = which == 0 ? glibc::exp(x[i]) : glibc::log(x[i]);
@@ -719,6 +723,8 @@ int launch_math_probe(int which, const double* x, double* y, long long n, cudaSt
     ELL_CUDA_TRY(cudaGetLastError());
     return ELLCUDA_OK;
 }
+
+#endif  // __CUDACC__
 
 int launch_batch_small(const BatchArgs& a, int oracle_id, cudaStream_t s, int sm_count, long long* launches) {
     const int m = a.mode;

@@ -1,7 +1,8 @@
 // tmem.cuh — tcgen05 tensor-memory helpers shared by the batched kernels that keep the shape matrix M in TMEM
 // (batch_lowpass.cu: n = 32; batch_ell64.cu: n <= 64).  TMEM is lane-addressed: a warp reaches only the 32 lanes of its own
 // quarter (warp % 4), at a warp-uniform column; 512 32-bit columns per SM, allocated per CTA.
-#pragma once
+#ifndef ELLCUDA_TMEM_CUH   // a classic guard: tests/cpp/tmem_emu.h defines it to put a host emulation in this header's place
+#define ELLCUDA_TMEM_CUH
 #include <cstdint>
 
 namespace ellcuda {
@@ -69,3 +70,5 @@ __device__ __forceinline__ void tm_free_all(uint32_t base, int warp) {
 }
 
 }  // namespace ellcuda
+
+#endif  // ELLCUDA_TMEM_CUH

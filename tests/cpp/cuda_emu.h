@@ -137,6 +137,17 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {   // ((hi:lo) >> (shift & 31)), low word
+    return (unsigned)(((((uint64_t)hi) << 32) | lo) >> (shift & 31));
+}
+static inline int __double2loint(double v) { uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)b; }
+static inline int __double2hiint(double v) { uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)(b >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double v;
+    std::memcpy(&v, &b, 8);
+    return v;
+}
 using std::min;
 
 namespace emu {

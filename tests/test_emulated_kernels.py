@@ -30,11 +30,18 @@ SRC = os.path.join(CPP, "emu_ellcta.cpp")
 SRC_ST = os.path.join(CPP, "emu_stable_large.cpp")
 SRC_BW = os.path.join(CPP, "emu_batch_warp.cpp")
 SRC_LMI = os.path.join(CPP, "emu_lmi.cpp")
+SRC_LP = os.path.join(CPP, "emu_lowpass32.cpp")
+SRC_E64 = os.path.join(CPP, "emu_ell64.cpp")
+SRC_SM = os.path.join(CPP, "emu_batch_small.cpp")
+LIB_SM = os.path.join(BUILD, "libemu_batch_small.so")
+LIB_E64, TSAN_E64 = os.path.join(BUILD, "libemu_ell64.so"), os.path.join(BUILD, "emu_ell64_tsan")
+LIB_LP, TSAN_LP = os.path.join(BUILD, "libemu_lowpass32.so"), os.path.join(BUILD, "emu_lowpass32_tsan")
 LIB_LMI, TSAN_LMI = os.path.join(BUILD, "libemu_lmi.so"), os.path.join(BUILD, "emu_lmi_tsan")
 LIB_BW, TSAN_BW = os.path.join(BUILD, "libemu_batch_warp.so"), os.path.join(BUILD, "emu_batch_warp_tsan")
 LIB, TSAN = os.path.join(BUILD, "libemu_ellcta.so"), os.path.join(BUILD, "emu_ellcta_tsan")
 LIB_ST, TSAN_ST = os.path.join(BUILD, "libemu_stable_large.so"), os.path.join(BUILD, "emu_stable_large_tsan")
-DEPS = [os.path.join(CPP, "cuda_emu.h")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "batch_warp.cu",
+DEPS = [os.path.join(CPP, "cuda_emu.h"), os.path.join(CPP, "tmem_emu.h"), os.path.join(CSRC, "batch_lowpass.cu"),
+        os.path.join(CSRC, "batch_ell64.cu"), os.path.join(CSRC, "batch_small.cu"), os.path.join(CSRC, "glibc_math.cuh")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "batch_warp.cu",
                                                                               "batch_stable.cu", "lmi_device.cuh", "common.cuh",
                                                                               "ell_calc.cuh")]
 
@@ -251,3 +258,144 @@ def test_lmi_kernel_no_data_race_under_thread_sanitizer():
     # loop's closing __syncwarp in its first round, is covered by the next step's); two re-checked here
     assert _races_with_dropped_barrier(exe, 2, "EMU_DROP_SYNCWARP")
     assert _races_with_dropped_barrier(exe, 22, "EMU_DROP_SYNCWARP")      # the two-rows-per-step LDL^T: end of a step
+
+
+# ------------------------------------------------------------------------------------------ the headline kernel (configs[2])
+def test_emulated_headline_kernel_equals_checker_and_golden(ref):  # csrc/batch_lowpass.cu with tensor memory emulated (tmem_emu.h)
+    import golden_cases
+    lib = C.CDLL(_build(LIB_LP, ["-O2", "-fPIC", "-shared"], SRC_LP))
+    lib.emu_lowpass32_solve.restype = C.c_int
+    lib.emu_lowpass32_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+
+    def solve(prob, variant=0):
+        out = BatchOutput.empty(prob.count, prob.n)
+        d, r = prob.to_desc(0), out.to_result()
+        assert lib.emu_lowpass32_solve(C.byref(d), C.byref(r), variant) == 0
+        return out
+    t = ref.lowpass_table(32)
+    prob = W.lowpass(13, t, max_iters=700)                 # more problems than emulated warps: the work queue's second round
+    want = ref.solve(prob)
+    for variant in (0, 1, 2):                              # ELLCUDA_LOWPASS_VARIANT: spectrum tail in shared memory / in TMEM
+        assert_parity(solve(prob, variant), want, exact=True, what=f"emulated lowpass32 variant {variant}")
+    prob.use_parallel_cut = False
+    prob.no_defer_trick = True
+    assert_parity(solve(prob), ref.solve(prob), exact=True, what="emulated lowpass32 flags")
+    bands = golden_cases.CASES["lowpass32_bands"](ref)     # short bands, empty transition band, edges on multiples of 32
+    g = solve(bands)
+    assert_parity(g, ref.solve(bands), exact=True, what="emulated lowpass32 band layouts")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    for f in ("num_iters", "exit_status", "gamma", "xc", "xbest"):
+        assert np.array_equal(getattr(g, f), gold[f"lowpass32_bands/{f}"], equal_nan=True), f
+
+
+def test_headline_kernel_no_data_race_under_thread_sanitizer():
+    """lanes share x, g, grad_t through shared memory (__syncwarp); warps share the SM's tensor memory (disjoint cells)"""
+    exe = _build(TSAN_LP, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER"], SRC_LP)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-4000:]
+    assert p.stdout.count("9 of 9 with xbest") == 2
+    # sensitivity: each of the first 20 __syncwarp calls and both start-up __syncthreads were dropped once by hand; all reported
+    assert _races_with_dropped_barrier(exe, 3, "EMU_DROP_SYNCWARP")
+    assert _races_with_dropped_barrier(exe, 0)               # the barrier that publishes the staged spectrum
+
+
+# ------------------------------------------------------------------------------------------ Ell with M in tensor memory, n <= 64
+def test_emulated_ell64_kernel_equals_checker(ref):  # csrc/batch_ell64.cu with tensor memory emulated
+    from ellalgo_rs_b200 import _abi as A
+    lib = C.CDLL(_build(LIB_E64, ["-O2", "-fPIC", "-shared"], SRC_E64))
+    lib.emu_ell64_solve.restype = C.c_int
+    lib.emu_ell64_solve.argtypes = [C.c_void_p, C.c_void_p]
+
+    def solve(prob):
+        out = BatchOutput.empty(prob.count, prob.n)
+        d, r = prob.to_desc(0), out.to_result()
+        assert lib.emu_ell64_solve(C.byref(d), C.byref(r)) == 0
+        return out
+    rng = np.random.default_rng(64)
+    for n, count, iters in ((33, 7, 120), (48, 9, 100), (64, 8, 100)):
+        prob = W.bowl(count, n=n, max_iters=iters)
+        assert_parity(solve(prob), ref.solve(prob), exact=True, what=f"emulated ell64 bowl n={n}")
+    n = 50
+    prob = W.bowl(5, n=n, max_iters=80)
+    prob.kappa0 = np.ones(1)
+    prob.mq0 = np.ascontiguousarray(100.0 * (np.eye(n)[None] + rng.uniform(-1, 1, (5, n, n)) / n))     # non-symmetric start
+    for nd in (False, True):
+        prob.no_defer_trick = nd
+        assert_parity(solve(prob), ref.solve(prob), exact=True, what=f"emulated ell64 bowl matrix start no_defer={nd}")
+    prob = W.lowpass(3, ref.lowpass_table(40), n=40, max_iters=400)
+    assert_parity(solve(prob), ref.solve(prob), exact=True, what="emulated ell64 lowpass n=40")
+    for make, oracle in ((lambda: W.lmi(5, n=64, m=16), A.ORACLE_LMI), (lambda: W.lmi(4, n=20, m=7), A.ORACLE_LMI_OLD),
+                         (lambda: W.lmi0(5, n=40, m=9), A.ORACLE_LMI0)):       # tests/lmi_tests.rs:174-225 run both spaces
+        prob = make()
+        prob.kind, prob.oracle_id, prob.max_iters = A.KIND_ELL, oracle, 150
+        g, r = solve(prob), ref.solve(prob)
+        assert_parity(g, r, exact=True, what=f"emulated ell64 LMI oracle {oracle} on Ell")
+    assert (g.exit_status == A.EXIT_FEASIBLE).any()
+
+
+def test_ell64_kernel_no_data_race_under_thread_sanitizer():
+    exe = _build(TSAN_E64, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER"], SRC_E64)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "LMI0 on Ell n=40 m=9: rc 0" in p.stdout and "7 of 7 with xbest" in p.stdout
+    # sensitivity: the first 16 __syncwarp calls were each dropped once by hand, 15 reported (the first only orders the zero fill
+    # of the vectors, which the first iteration's own __syncwarp covers); one re-checked here
+    assert _races_with_dropped_barrier(exe, 2, "EMU_DROP_SYNCWARP")
+
+
+# ------------------------------------------------------------------------------------------ the n = 2 kernels: every pinned count
+def test_emulated_n2_kernels_reproduce_every_pinned_count(ref):  # csrc/batch_small.cu through its own dispatch table
+    import math
+    from ellalgo_rs_b200 import _abi as A
+    from ellalgo_rs_b200.problem import BatchProblem
+    lib = C.CDLL(_build(LIB_SM, ["-O2", "-fPIC", "-shared", "-mfma"], SRC_SM))    # -mfma: glibc's exp/log use a true fma
+    lib.emu_batch_small_solve.restype = C.c_int
+    lib.emu_batch_small_solve.argtypes = [C.c_void_p, C.c_void_p]
+
+    def solve(prob):
+        out = BatchOutput.empty(prob.count, prob.n)
+        d, r = prob.to_desc(0), out.to_result()
+        assert lib.emu_batch_small_solve(C.byref(d), C.byref(r)) == 0
+        return out
+
+    def check(prob, what, pinned=None):
+        g = solve(prob)
+        assert_parity(g, ref.solve(prob), exact=True, what=what)
+        if pinned is not None:
+            assert g.num_iters[0] == pinned, f"{what}: {g.num_iters[0]} iterations, the reference's test pins {pinned}"
+        return g
+    inf = math.inf
+    check(W.example1(), "example1", 25)                                                            # src/example1.rs:39-50
+    check(BatchProblem(oracle_id=A.ORACLE_EXAMPLE1_RR, n=2, count=3, kappa0=10.0, gamma0=-inf, tolerance=1e-10), "example1_rr", 25)
+    check(BatchProblem(oracle_id=A.ORACLE_EXAMPLE4, n=2, count=3, kappa0=10.0, gamma0=-inf, tolerance=1e-10), "example4", 82)
+    g = check(W.profit(300), "profit", 83)                                                         # profit_oracle.rs:207-223
+    assert g.xbest[0, 0] <= math.log(30.5)
+    p = W.profit(1)
+    p.oracle_id = A.ORACLE_PROFIT_RB
+    p.params = np.concatenate([W.PROFIT_REF, [0.003, 0.007, 1.0, 1.0, 1.0]])
+    check(p, "profit_rb", 90)                                                                      # :225-242
+    p = W.profit(70)
+    p.oracle_id, p.mode = A.ORACLE_PROFIT_Q, A.MODE_OPTIM_Q
+    check(p, "profit_q", 29)                                                                       # :244-260
+    check(BatchProblem(oracle_id=A.ORACLE_QUASICVX, n=2, count=1, kappa0=1.0, diag0=[10.0, 10.0], gamma0=0.0, tolerance=1e-8),
+          "quasicvx", 35)                                                                          # src/quasicvx.rs:61-78
+    check(BatchProblem(oracle_id=A.ORACLE_QUASICVX, n=2, count=1, kind=A.KIND_ELLSTABLE, kappa0=1.0, diag0=[10.0, 10.0], gamma0=0.0,
+                       tolerance=1e-8), "quasicvx on EllStable", 49)
+    g = check(BatchProblem(oracle_id=A.ORACLE_EXAMPLE3, n=2, count=1, mode=A.MODE_BSEARCH, kappa0=100.0, gamma0=-100.0,
+                           params=[100.0, 1e-8, 2000.0], tolerance=1e-8), "bsearch example3", 34)  # src/example3.rs:68-85
+    assert g.has_xbest[0] == 1
+    for kind in (A.KIND_ELL, A.KIND_ELLSTABLE):                                                    # tests/cutting_plane_tests.rs, example2
+        for what, kw, pinned in (("always_cut_feas", dict(oracle_id=A.ORACLE_ALWAYS_CUT, mode=A.MODE_FEAS, kappa0=10.0, max_iters=200), 2),
+                                 ("always_cut_q", dict(oracle_id=A.ORACLE_ALWAYS_CUT, mode=A.MODE_OPTIM_Q, kappa0=10.0, gamma0=0.0, max_iters=5), 2),
+                                 ("halfplane", dict(oracle_id=A.ORACLE_HALFPLANE, mode=A.MODE_FEAS, kappa0=10.0, max_iters=200), 0),
+                                 ("optim_box", dict(oracle_id=A.ORACLE_OPTIM_BOX, kappa0=10.0, gamma0=0.0, max_iters=200), None),
+                                 ("optim_box_q", dict(oracle_id=A.ORACLE_OPTIM_BOX, mode=A.MODE_OPTIM_Q, kappa0=10.0, gamma0=0.0, max_iters=200), None),
+                                 ("example2", dict(oracle_id=A.ORACLE_EXAMPLE2, mode=A.MODE_FEAS, kappa0=10.0), 1),
+                                 ("example2_inf", dict(oracle_id=A.ORACLE_EXAMPLE2, mode=A.MODE_FEAS, kappa0=10.0, xc0=[100.0, 100.0]), 0)):
+            check(BatchProblem(n=2, count=3, kind=kind, **kw), f"{what} kind={kind}", pinned if kind == A.KIND_ELL else None)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))                         # and the committed vectors
+    import golden_cases
+    for name in ("example1", "profit", "profit_q", "quasicvx_stable"):
+        g = solve(golden_cases.CASES[name](ref))
+        for f in ("num_iters", "exit_status", "gamma", "xc", "xbest"):
+            assert np.array_equal(getattr(g, f), gold[f"{name}/{f}"], equal_nan=True), f"{name}/{f}"
