@@ -105,14 +105,18 @@ def _tsan_exe():
     return _build(TSAN, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER"])
 
 
-def _races_with_dropped_barrier(exe, k, var="EMU_DROP_BARRIER"):
-    """every emulated thread skips its k-th __syncthreads (or __syncwarp); returns whether ThreadSanitizer reported a data race"""
-    try:
-        p = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, **{var: str(k)}))
-        err = p.stderr
-    except subprocess.TimeoutExpired as e:            # without the barrier the threads may also diverge and hang
-        err = (e.stderr or b"").decode() if isinstance(e.stderr, bytes) else (e.stderr or "")
-    return "WARNING: ThreadSanitizer: data race" in err
+def _races_with_dropped_barrier(exe, k, var="EMU_DROP_BARRIER", attempts=3):
+    """every emulated thread skips its k-th __syncthreads (or __syncwarp); returns whether ThreadSanitizer reported a data race.
+    Detection depends on the two unordered accesses really overlapping in some schedule, so a miss is retried."""
+    for _ in range(attempts):
+        try:
+            p = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, **{var: str(k)}))
+            err = p.stderr
+        except subprocess.TimeoutExpired as e:            # without the barrier the threads may also diverge and hang
+            err = (e.stderr or b"").decode() if isinstance(e.stderr, bytes) else (e.stderr or "")
+        if "WARNING: ThreadSanitizer: data race" in err:
+            return True
+    return False
 
 
 def test_no_data_race_under_thread_sanitizer():
