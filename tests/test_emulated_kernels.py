@@ -46,8 +46,29 @@ DEPS = [os.path.join(CPP, "cuda_emu.h"), os.path.join(CPP, "tmem_emu.h"), os.pat
                                                                               "ell_calc.cuh")]
 
 
+_TSAN_OK = None
+
+
+def _have_tsan():
+    """g++ -fsanitize=thread can build and run a trivial program here (the runtime is an optional package)"""
+    global _TSAN_OK
+    if _TSAN_OK is None:
+        os.makedirs(BUILD, exist_ok=True)
+        probe = os.path.join(BUILD, "tsan_probe")
+        with open(probe + ".cpp", "w") as f:
+            f.write("int main() { return 0; }\n")
+        try:
+            subprocess.run(["g++", "-fsanitize=thread", probe + ".cpp", "-o", probe], check=True, capture_output=True)
+            _TSAN_OK = subprocess.run([probe], capture_output=True, timeout=60).returncode == 0
+        except Exception:
+            _TSAN_OK = False
+    return _TSAN_OK
+
+
 def _build(out, extra, src=SRC):
     os.makedirs(BUILD, exist_ok=True)
+    if "-fsanitize=thread" in extra and not _have_tsan():
+        pytest.skip("no ThreadSanitizer runtime for g++ on this box")
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS + [src]):
         subprocess.run(["g++", "-std=c++17", "-g", "-ffp-contract=off", "-Wno-attributes", "-Wno-unknown-pragmas", "-I", CUDA_INC, src] + extra +
                        ["-o", out, "-lpthread", "-ldl"], check=True, capture_output=True, text=True)
