@@ -225,8 +225,8 @@ __global__ void __launch_bounds__(MAXT) batch_stable_kernel(const BatchArgs a, i
 __global__ void __launch_bounds__(32) stable_single_kernel(double* __restrict__ qu_g, double* __restrict__ xc_g, double* __restrict__ scal,
                                                            int* __restrict__ status_out, const double* __restrict__ g, int n,
                                                            CalcConsts cc, int which, Cut cut) {
-    __shared__ __align__(16) double s_qu[kNMax * (kNMax + 1) / 2];
-    __shared__ __align__(16) double s_vec[3 * kNMax];
+    ELL_STATIC_SHARED __align__(16) double s_qu[kNMax * (kNMax + 1) / 2];
+    ELL_STATIC_SHARED __align__(16) double s_vec[3 * kNMax];
     const int lane = threadIdx.x;
     const int tri = n * (n + 1) / 2;
     for (int e = lane; e < tri; e += 32) s_qu[e] = qu_g[e];

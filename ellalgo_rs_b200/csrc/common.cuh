@@ -64,6 +64,14 @@ inline int env_int_once(const char* name, int dflt, int* cache, bool* have) {
 }
 #define ELL_ENV_INT(name, dflt) ([]() -> int { static int v = 0; static bool have = false; return ::ellcuda::env_int_once(name, dflt, &v, &have); }())
 
+// `__shared__` for a kernel's static shared variables.  nvcc sees exactly `__shared__`; the host emulation of the kernels
+// (tests/cpp/emu_*.cpp, which compile these sources with g++ and run one emulated CTA at a time) sees `static`.
+#ifdef __CUDACC__
+#define ELL_STATIC_SHARED __shared__
+#else
+#define ELL_STATIC_SHARED static
+#endif
+
 void set_error(const std::string& msg);
 void keep_mempool(int dev);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);

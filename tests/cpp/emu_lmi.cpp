@@ -57,6 +57,17 @@ extern "C" int emu_lmi_solve(const ell_batch_desc* d, const ell_batch_result* r)
     return ELLCUDA_OK;
 }
 
+// one update_core of the single EllStable handle with n <= 64 (stable_single_kernel: one warp, the packed factor staged in
+// static shared memory); arguments as emu_stable_large_update
+extern "C" int emu_stable_single_update(double* qu, double* xc, double* scal, int* status, const double* g, int n, int use_parallel,
+                                        int which, double beta0, int has_beta1, double beta1) {
+    if (n < 1 || n > kNMax) return ELLCUDA_E_ARG;
+    const CalcConsts cc = CalcConsts::make(n, use_parallel);
+    const Cut cut = has_beta1 > 0 ? parallel_cut(beta0, beta1) : single_cut(beta0);
+    emu::run_cta(32, [&](int) { stable_single_kernel(qu, xc, scal, status, g, n, cc, which, cut); });
+    return ELLCUDA_OK;
+}
+
 #ifdef EMU_MAIN
 static int solve(const char* name, ell_batch_desc d, int count, int n) {
     std::vector<double> xbest((size_t)count * n, 0.0), tsq(count), xc((size_t)count * n), kappa(count);
@@ -106,6 +117,21 @@ int main() {
         for (int j = 0; j < m; ++j) table[(size_t)i * m + j] = (i == j ? 1.0 : 0.0) + 0.25 * table[(size_t)i * m + j];
     d.table_len = (int64_t)n * m * m;
     bad |= solve("LMI0 diagonal start", d, count, n);
+    {   // the single handle (n <= 64): three updates of an n = 40 factor, one of them failing
+        const int ns = 40;
+        std::vector<double> qu((size_t)ns * (ns + 1) / 2), xs(ns), g(ns), scal{2.5, 0.0};
+        size_t e = 0;
+        for (int r = 0; r < ns; ++r)
+            for (int c = r; c < ns; ++c) qu[e++] = c == r ? 1.0 + 0.01 * r : 1e-3 * std::sin(1.0 + 3.0 * r + 7.0 * c);
+        for (int i = 0; i < ns; ++i) xs[i] = std::cos(0.3 * i);
+        int status = -1, step = 0;
+        const struct { int which; double b0; int has; double b1; } cuts[] = {{0, 0.01, 1, 0.10}, {0, 1e6, -1, 0.0}, {1, 0.0, -1, 0.0}};
+        for (const auto& c : cuts) {
+            for (int i = 0; i < ns; ++i) g[i] = std::sin(0.7 * i + step) / std::sqrt((double)ns);
+            bad |= emu_stable_single_update(qu.data(), xs.data(), scal.data(), &status, g.data(), ns, 1, c.which, c.b0, c.has, c.b1);
+            std::printf("single handle step %d: status %d, kappa %.17g\n", step++, status, scal[0]);
+        }
+    }
     return bad;
 }
 #endif

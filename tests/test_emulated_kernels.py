@@ -159,12 +159,15 @@ def _pack_upper(mq):
     return np.ascontiguousarray(np.concatenate([mq[r, r:] for r in range(n)]))
 
 
-@pytest.mark.parametrize("n,start", [(70, "upper"), (100, "diag"), (65, "scalar")])
-def test_emulated_ellstable_update_equals_checker(ref, n, start):  # src/ell_stable.rs:52-125 through stable_large_body
+@pytest.mark.parametrize("n,start", [(70, "upper"), (100, "diag"), (65, "scalar"), (7, "diag"), (33, "upper"), (64, "upper")])
+def test_emulated_ellstable_update_equals_checker(ref, n, start):  # src/ell_stable.rs:52-125: one CTA (n > 64) / one warp (n <= 64)
     from ellalgo_rs_b200 import _abi as A
-    lib = C.CDLL(_build(LIB_ST, ["-O2", "-fPIC", "-shared"], SRC_ST))
-    lib.emu_stable_large_update.restype = C.c_int
-    lib.emu_stable_large_update.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    if n > 64:
+        update = C.CDLL(_build(LIB_ST, ["-O2", "-fPIC", "-shared"], SRC_ST)).emu_stable_large_update
+    else:
+        update = C.CDLL(_build(LIB_LMI, ["-O2", "-fPIC", "-shared"], SRC_LMI)).emu_stable_single_update
+    update.restype = C.c_int
+    update.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
     rng = np.random.default_rng(n)
     xc = rng.uniform(-1, 1, n)
     kappa, mq, diag = 3.0, None, None
@@ -179,8 +182,7 @@ def test_emulated_ellstable_update_equals_checker(ref, n, start):  # src/ell_sta
             (A.UPDATE_BIAS, 0.02, -1, 0.0), (A.UPDATE_CENTRAL, 0.0, 1, 0.05)]
     for k, (which, b0, has, b1) in enumerate(cuts):
         g = np.ascontiguousarray(rng.uniform(-1, 1, n) / np.sqrt(n))
-        assert lib.emu_stable_large_update(qu.ctypes.data, x.ctypes.data, scal.ctypes.data, status.ctypes.data, g.ctypes.data, n, 1,
-                                           which, b0, has, b1) == 0
+        assert update(qu.ctypes.data, x.ctypes.data, scal.ctypes.data, status.ctypes.data, g.ctypes.data, n, 1, which, b0, has, b1) == 0
         st = s.update(which, g, b0, b1 if has > 0 else None, single=has < 0)
         r = s.state()
         assert int(status[0]) == st, f"step {k}: status"
@@ -279,6 +281,7 @@ def test_lmi_kernel_no_data_race_under_thread_sanitizer():
     p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-4000:]
     assert "LMI0 diagonal start: rc 0" in p.stdout and "4 of 4 feasible" in p.stdout
+    assert "single handle step 1: status 1" in p.stdout and "single handle step 2: status 0" in p.stdout
     # sensitivity: the first 48 __syncwarp calls were each dropped once by hand and 47 drops were reported (the 48th, the pair
     # loop's closing __syncwarp in its first round, is covered by the next step's); two re-checked here
     assert _races_with_dropped_barrier(exe, 2, "EMU_DROP_SYNCWARP")
