@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "stream_ptx.cuh"
 
 namespace ellcuda {
 namespace {
@@ -33,50 +34,7 @@ struct Scal {  // device-resident scalars of the Ell (src/ell.rs:9-16) + the def
     int _pad;       // publishing, so that the peers time out too instead of consuming a half-updated state
 };
 
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, void* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
-                 "r"(smem_u32(src))
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, void* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// (the inline PTX — mbarrier, TMA / bulk copies, flagged lines, programmatic dependent launch — is in stream_ptx.cuh)
 
 // ------------------------------------------------------------------------------------------------ kernels
 // Peer exchange (row-sharded handles attached with ellcuda_exchange_attach): the sweep CTA that completes a block of
@@ -105,27 +63,6 @@ __host__ __device__ inline uint4* xblk_parts(double* blk, long long n, int parit
 __host__ __device__ inline uint4* xblk_lines(double* blk, long long n, int parity) {
     return reinterpret_cast<uint4*>(blk + xblk_plain_doubles(n)) + (long long)parity * n;
 }
-__device__ __forceinline__ void ll_store(uint4* line, double v, unsigned flag) {
-    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
-}
-// polls until both halves of the line carry `flag`; false on timeout (~10 s) so that a lost peer cannot hang the GPU
-__device__ __forceinline__ bool ll_load(const uint4* line, unsigned flag, double& v) {
-    unsigned a, fa, b, fb;
-    long long t0 = 0;
-    for (int spins = 0;; ++spins) {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(line) : "memory");
-        if (fa == flag && fb == flag) break;
-        if (spins == 64) t0 = clock64();
-        if (spins > 64) {
-            if (clock64() - t0 > 20000000000LL) return false;
-            __nanosleep(64);
-        }
-    }
-    v = __hiloint2double((int)b, (int)a);
-    return true;
-}
-
 // MODE 0: every row of the tile is above the block's columns (i < c):   update = (ratio·gt[c]) · gt[i]
 // MODE 1: every row is at or below them (i >= c):                        update = (ratio·gt[i]) · gt[c]
 // MODE 2: the tile crosses the diagonal: choose per element.             (src/ell.rs:118-127: hi = max, lo = min)
@@ -170,11 +107,6 @@ __device__ __forceinline__ void tile_rows(double* __restrict__ tile_raw, const d
         if (TWO) acc1 += m.y * gi;
     }
 }
-
-// Programmatic dependent launch: a kernel launched with the attribute may start while its predecessor in the stream is still
-// running; everything before pdl_wait() must not touch what the predecessor writes.  pdl_trigger() lets the successor start.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ tensor map
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

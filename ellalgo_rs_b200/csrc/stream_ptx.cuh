@@ -1,0 +1,92 @@
+// stream_ptx.cuh — the inline PTX of the large-n kernels: mbarrier, TMA tensor / bulk copies, the flagged 16-byte lines of
+// the peer exchange, programmatic dependent launch.  A header of its own, with a classic include guard, so that
+// tests/cpp/stream_ptx_emu.h can define the guard and put a host emulation of exactly these functions in its place.
+#ifndef ELLCUDA_STREAM_PTX_CUH
+#define ELLCUDA_STREAM_PTX_CUH
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ellcuda {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, void* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void ll_store(uint4* line, double v, unsigned flag) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+// one look at a line: {lo32, flag, hi32, flag}
+__device__ __forceinline__ void ll_peek(const uint4* line, unsigned (&w)[4]) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(line) : "memory");
+}
+// polls until both halves of the line carry `flag`; false on timeout (~10 s) so that a lost peer cannot hang the GPU
+__device__ __forceinline__ bool ll_load(const uint4* line, unsigned flag, double& v) {
+    unsigned a, fa, b, fb;
+    long long t0 = 0;
+    for (int spins = 0;; ++spins) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(line) : "memory");
+        if (fa == flag && fb == flag) break;
+        if (spins == 64) t0 = clock64();
+        if (spins > 64) {
+            if (clock64() - t0 > 20000000000LL) return false;
+            __nanosleep(64);
+        }
+    }
+    v = __hiloint2double((int)b, (int)a);
+    return true;
+}
+
+// Programmatic dependent launch: a kernel launched with the attribute may start while its predecessor in the stream is still
+// running; everything before pdl_wait() must not touch what the predecessor writes.  pdl_trigger() lets the successor start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+}  // namespace
+}  // namespace ellcuda
+
+#endif  // ELLCUDA_STREAM_PTX_CUH

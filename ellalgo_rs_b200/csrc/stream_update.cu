@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(32 * kW) sweep_kernel(const __grid_constant__ 
     if (ntiles > 0) {
         if (threadIdx.x == 0) {
             for (int s = 0; s < kStages; ++s) mbar_init(&ring.bars[s], 2);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_fence_init();
             for (int t = 0; t < pre; ++t) ring.issue_m(&map, t, row_lo + (long long)t * kRows, (long long)cb * kCols);
         }
         cta_sync<kW>();
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const uint4* line = lines + k + (long long)u * kFinThreads;
-                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]) : "l"(line) : "memory");
+                    ll_peek(line, w[u]);
                     gk[u] = g[k + (long long)u * kFinThreads];
                 }
 #pragma unroll
