@@ -161,7 +161,7 @@ __device__ __forceinline__ void sweep_body(const CUtensorMap* map, const SweepAr
 template <int kCols, int kRows, int kStages, int kW>
 __global__ void __launch_bounds__(32 * kW) sweep_kernel(const __grid_constant__ CUtensorMap map, const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ unsigned s_prev;
+    ELL_STATIC_SHARED unsigned s_prev;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cb = blockIdx.x, seg = blockIdx.y;
     const long long rows_per = ((a.n + a.nseg - 1) / a.nseg + kRows - 1) / kRows * kRows;
@@ -246,19 +246,22 @@ __global__ void __launch_bounds__(32 * kW) sweep_kernel(const __grid_constant__ 
 // and updates its slice of xc / pend; the CTA that arrives last — when every other CTA has read `sc` — writes the new
 // scalars back, so no CTA can observe a half-updated state.  With peer exchange grad_t is read from this rank's flagged
 // lines (polling until every slab has arrived), otherwise from the plain buffer the sweep (or the caller's allgather) filled.
-constexpr int kFinThreads = 1024;
+#ifndef ELLCUDA_FIN_THREADS
+#define ELLCUDA_FIN_THREADS 1024   // the host emulation under ThreadSanitizer builds with 128 (it tracks <= 256 running threads)
+#endif
+constexpr int kFinThreads = ELLCUDA_FIN_THREADS;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)
 __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __restrict__ g, double* blk, double* __restrict__ xc,
                                                              double2* __restrict__ pend, Scal* sc, unsigned* arrivals, long long n,
                                                              CalcConsts cc, int which, Cut cut, int no_defer, int reduce_mode,
                                                              int nranks) {
-    __shared__ double prod[kFinChunk];
-    __shared__ double s_omega;
-    __shared__ double s_kappa_in;
-    __shared__ unsigned long long s_epoch;
-    __shared__ int s_timeout;
-    __shared__ Scal s_out;
-    __shared__ double s_roo;
+    ELL_STATIC_SHARED double prod[kFinChunk];
+    ELL_STATIC_SHARED double s_omega;
+    ELL_STATIC_SHARED double s_kappa_in;
+    ELL_STATIC_SHARED unsigned long long s_epoch;
+    ELL_STATIC_SHARED int s_timeout;
+    ELL_STATIC_SHARED Scal s_out;
+    ELL_STATIC_SHARED double s_roo;
     const int tid = threadIdx.x;
     pdl_wait();      // the sweep of this update is complete (its M stores too)
     pdl_trigger();   // the next update's sweep may start its prologue: barriers and the first tiles of M
@@ -434,6 +437,7 @@ constexpr size_t sweep_smem(int cols, int rows, int stages) { return (size_t)sta
 namespace ellcuda {
 namespace {
 
+#ifdef __CUDACC__   // host side: left out when tests/cpp/emu_stream.cpp compiles the kernels of this file for the host
 void free_ctx(ellcuda_ctx* h) {
     if (!h) return;
     for (size_t r = h->parts.size(); r-- > 0;) free_ctx(h->parts[r]);   // reverse: a later slab may borrow an earlier one's stream
@@ -587,6 +591,8 @@ int enqueue_begin(ellcuda_ctx* h, const double* g_dev, double* plain_out = nullp
     h->launches += 1;
     return ELLCUDA_OK;
 }
+#endif  // __CUDACC__
+
 
 __global__ void clear_pending_kernel(Scal* sc) { sc->pending = 0; sc->scale = 1.0; }
 
@@ -606,6 +612,8 @@ __global__ void __launch_bounds__(1024) seq_sum_kernel(const double* __restrict_
     if (threadIdx.x == 0) *out = acc;
 }
 
+#ifdef __CUDACC__
+
 int flush_pending(ellcuda_ctx* h) {  // make S hold the reference's `mq` exactly
     int rc = enqueue_begin(h, nullptr);
     if (rc) return rc;
@@ -615,11 +623,14 @@ int flush_pending(ellcuda_ctx* h) {  // make S hold the reference's `mq` exactly
     return ELLCUDA_OK;
 }
 
+#endif  // __CUDACC__
+
 }  // namespace
 }  // namespace ellcuda
 
 using namespace ellcuda;
 
+#ifdef __CUDACC__
 extern "C" {
 // ---- EllStable as a single host-driven search space (src/ell_stable.rs:9-35, 128-210), n <= 2048 -----------------------
 static int create_stable(const ell_create_desc* d, ell_handle* out) {
@@ -1351,3 +1362,4 @@ int64_t ellcuda_handle_launch_count(ell_handle h) {
 int32_t ellcuda_group_size(ell_handle h) { return !h ? 0 : h->parts.empty() ? 1 : (int32_t)h->parts.size(); }
 
 }  // extern "C"
+#endif  // __CUDACC__
