@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(32 * kW) sweep_kernel(const __grid_constant__ 
 // scalars back, so no CTA can observe a half-updated state.  With peer exchange grad_t is read from this rank's flagged
 // lines (polling until every slab has arrived), otherwise from the plain buffer the sweep (or the caller's allgather) filled.
 #ifndef ELLCUDA_FIN_THREADS
-#define ELLCUDA_FIN_THREADS 1024   // the host emulation under ThreadSanitizer builds with 128 (it tracks <= 256 running threads)
+#define ELLCUDA_FIN_THREADS 1024   // the host emulation under ThreadSanitizer builds with 128 (it tracks <= 256 running threads);
+                                   // the fixed tree of reduce_mode > 0 below is written for the 32 warps of 1024 threads
 #endif
 constexpr int kFinThreads = ELLCUDA_FIN_THREADS;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <thread>
 #include <vector>
@@ -148,12 +149,22 @@ static inline double __hiloint2double(int hi, int lo) {
     std::memcpy(&v, &b, 8);
     return v;
 }
+static inline double __ldcg(const double* p) { return *p; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
+static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
+static inline long long clock64() { return (long long)std::clock(); }
+static inline void __nanosleep(unsigned) { sched_yield(); }
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
 using std::min;
 
 namespace emu {
 // runs fn(tid) on nt concurrent OS threads that form one emulated CTA
 template <class F>
-inline void run_cta(int nt, F fn) {
+inline void run_cta(int nt, F fn, EmuDim3 block = EmuDim3{0, 0, 0}, EmuDim3 grid = EmuDim3{1, 1, 1}) {
     Cta c;
     const size_t warps = (size_t)(nt + 31) / 32;
     for (auto& b : c.all) pthread_barrier_init(&b, nullptr, nt);
@@ -163,13 +174,14 @@ inline void run_cta(int nt, F fn) {
     c.slot.assign(32 * warps, 0);
     std::vector<std::thread> ts;
     for (int t = 0; t < nt; ++t)
-        ts.emplace_back([&c, &fn, t, nt] {
+        ts.emplace_back([&c, &fn, t, nt, block, grid] {
             cta = &c;
             tid = t;
             warp_rounds = 0;
             quiet_sense = 0;
             threadIdx.x = (unsigned)t; threadIdx.y = threadIdx.z = 0;
-            blockIdx.x = blockIdx.y = blockIdx.z = 0;
+            blockIdx = block;
+            gridDim = grid;
             blockDim.x = (unsigned)nt;
             fn(t);
         });

@@ -33,6 +33,8 @@ SRC_LMI = os.path.join(CPP, "emu_lmi.cpp")
 SRC_LP = os.path.join(CPP, "emu_lowpass32.cpp")
 SRC_E64 = os.path.join(CPP, "emu_ell64.cpp")
 SRC_SM = os.path.join(CPP, "emu_batch_small.cpp")
+SRC_STR = os.path.join(CPP, "emu_stream.cpp")
+LIB_STR, TSAN_STR = os.path.join(BUILD, "libemu_stream.so"), os.path.join(BUILD, "emu_stream_tsan")
 LIB_SM = os.path.join(BUILD, "libemu_batch_small.so")
 LIB_E64, TSAN_E64 = os.path.join(BUILD, "libemu_ell64.so"), os.path.join(BUILD, "emu_ell64_tsan")
 LIB_LP, TSAN_LP = os.path.join(BUILD, "libemu_lowpass32.so"), os.path.join(BUILD, "emu_lowpass32_tsan")
@@ -41,7 +43,8 @@ LIB_BW, TSAN_BW = os.path.join(BUILD, "libemu_batch_warp.so"), os.path.join(BUIL
 LIB, TSAN = os.path.join(BUILD, "libemu_ellcta.so"), os.path.join(BUILD, "emu_ellcta_tsan")
 LIB_ST, TSAN_ST = os.path.join(BUILD, "libemu_stable_large.so"), os.path.join(BUILD, "emu_stable_large_tsan")
 DEPS = [os.path.join(CPP, "cuda_emu.h"), os.path.join(CPP, "tmem_emu.h"), os.path.join(CSRC, "batch_lowpass.cu"),
-        os.path.join(CSRC, "batch_ell64.cu"), os.path.join(CSRC, "batch_small.cu"), os.path.join(CSRC, "glibc_math.cuh")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "batch_warp.cu",
+        os.path.join(CSRC, "batch_ell64.cu"), os.path.join(CSRC, "batch_small.cu"), os.path.join(CSRC, "glibc_math.cuh"),
+        os.path.join(CPP, "stream_ptx_emu.h"), os.path.join(CSRC, "stream_update.cu"), os.path.join(CSRC, "stream_common.cuh")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "batch_warp.cu",
                                                                               "batch_stable.cu", "lmi_device.cuh", "common.cuh",
                                                                               "ell_calc.cuh")]
 
@@ -427,3 +430,103 @@ def test_emulated_n2_kernels_reproduce_every_pinned_count(ref):  # csrc/batch_sm
         g = solve(golden_cases.CASES[name](ref))
         for f in ("num_iters", "exit_status", "gamma", "xc", "xbest"):
             assert np.array_equal(getattr(g, f), gold[f"{name}/{f}"], equal_nan=True), f"{name}/{f}"
+
+
+# ------------------------------------------------------------------------------------------ the large-n path (configs[4])
+class _EmuEll:
+    """Ell::update_core through the emulated sweep_kernel + finish_kernel (tests/cpp/emu_stream.cpp)"""
+
+    def __init__(self, lib, n, kappa, xc, mq=None, diag=None, no_defer=False, use_parallel=True, reduce_mode=0, cols=0, rows=64,
+                 warps=1, ll=False):
+        self.lib, self.n = lib, n
+        mq = None if mq is None else np.ascontiguousarray(mq, dtype=np.float64)
+        diag = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
+        xc = np.ascontiguousarray(xc, dtype=np.float64)
+        self.h = lib.emu_ell_new(n, kappa, None if mq is None else mq.ctypes.data, None if diag is None else diag.ctypes.data,
+                                 xc.ctypes.data, int(no_defer), int(use_parallel), reduce_mode, cols, rows, warps, int(ll))
+
+    def update(self, which, g, b0, b1=None, single=True):
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        return self.lib.emu_ell_update(self.h, which, g.ctypes.data, float(b0), 1 if b1 is not None else (-1 if single else 0),
+                                       0.0 if b1 is None else float(b1))
+
+    def state(self):
+        xc, mq = np.zeros(self.n), np.zeros((self.n, self.n))
+        k, t = C.c_double(), C.c_double()
+        self.lib.emu_ell_state(self.h, xc.ctypes.data, mq.ctypes.data, C.byref(k), C.byref(t))
+        return dict(xc=xc, mq=mq, kappa=k.value, tsq=t.value)
+
+    def dot_mv(self, x):
+        x, y = np.ascontiguousarray(x, dtype=np.float64), np.zeros(self.n)
+        self.lib.emu_ell_dot_mv(self.h, x.ctypes.data, y.ctypes.data)
+        return y
+
+    def __del__(self):
+        self.lib.emu_ell_free(self.h)
+
+
+@pytest.fixture(scope="module")
+def emu_stream():
+    lib = C.CDLL(_build(LIB_STR, ["-O2", "-fPIC", "-shared"], SRC_STR))
+    lib.emu_ell_new.restype = C.c_void_p
+    lib.emu_ell_new.argtypes = [C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7
+    lib.emu_ell_update.restype = C.c_int
+    lib.emu_ell_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_double]
+    lib.emu_ell_state.argtypes = [C.c_void_p] * 5
+    lib.emu_ell_dot_mv.argtypes = [C.c_void_p] * 3
+    lib.emu_ell_free.argtypes = [C.c_void_p]
+    return lib
+
+
+LARGE_N_VARIANTS = [  # n, reduce_mode, cols, tile rows, warps, flagged lines, no_defer, start
+    (150, 0, 64, 64, 1, False, False, "scalar"), (129, 0, 64, 64, 2, True, False, "diag"), (100, 0, 32, 64, 1, True, True, "dense"),
+    (90, 0, 16, 64, 1, False, False, "dense"), (140, 0, 64, 32, 1, False, True, "scalar"), (64, 0, 0, 64, 1, False, False, "dense"),
+    (200, 3, 64, 64, 1, True, False, "diag"), (130, 2, 32, 64, 1, False, True, "dense"), (77, 0, 0, 64, 1, True, False, "scalar")]
+
+
+@pytest.mark.parametrize("n,reduce_mode,cols,rows,warps,ll,no_defer,start", LARGE_N_VARIANTS)
+def test_emulated_large_n_update_equals_checker(ref, emu_stream, n, reduce_mode, cols, rows, warps, ll, no_defer, start):
+    """src/ell.rs:97-137 through sweep_kernel + finish_kernel: bit for bit in reduce_mode 0, 1e-9 with row segments"""
+    from ellalgo_rs_b200 import _abi as A
+    rng = np.random.default_rng(n + reduce_mode)
+    xc = rng.uniform(-1, 1, n)
+    kappa, mq, diag = 2.5, None, None
+    if start == "diag":
+        kappa, diag = 1.0, rng.uniform(0.5, 2.0, n)
+    elif start == "dense":
+        a = rng.uniform(-1, 1, (n, n)) / n
+        kappa, mq = 1.5, np.eye(n) + a + a.T
+    e = _EmuEll(emu_stream, n, kappa, xc, mq=mq, diag=diag, no_defer=no_defer, reduce_mode=reduce_mode, cols=cols, rows=rows, warps=warps, ll=ll)
+    s = ref.Space(A.KIND_ELL, n, kappa=kappa, mq=mq, diag=diag, xc=xc, no_defer_trick=no_defer)
+    exact = reduce_mode == 0
+    cuts = [(A.UPDATE_BIAS, 0.01, 0.10, False), (A.UPDATE_CENTRAL, 0.0, None, True), (A.UPDATE_BIAS, 1e6, None, True),      # 3rd: NoSoln
+            (A.UPDATE_BIAS, 0.02, None, True), (A.UPDATE_Q, -0.5, None, False), (A.UPDATE_CENTRAL, 0.0, 0.05, False)]
+    for k, (which, b0, b1, single) in enumerate(cuts):
+        g = rng.uniform(-1, 1, n) / np.sqrt(n)
+        assert e.update(which, g, b0, b1, single) == s.update(which, g, b0, b1, single), f"step {k}: status"
+    got, want = e.state(), s.state()
+    for f in ("tsq", "kappa", "xc", "mq"):
+        if exact:
+            assert np.array_equal(got[f], want[f]), f"{f} not bit-identical"
+        else:
+            assert np.allclose(got[f], want[f], rtol=1e-9, atol=1e-12), f
+    if exact:                                             # Arr::dot_mv on the handle (power iteration / CG use it): column sums of M
+        x = rng.uniform(-1, 1, n)
+        m = want["mq"]
+        y = np.zeros(n)
+        for j in range(n):                                # out[i] = sum_j M[i][j] x[j], j ascending from 0.0 (src/arr.rs:426-442)
+            y = y + m[:, j] * x[j]
+        assert np.array_equal(e.dot_mv(x), y)
+
+
+def test_large_n_kernels_no_data_race_under_thread_sanitizer():
+    """the mbarrier hand-off of the TMA ring, the CTA-wide staging of finish's ordered sum, the flagged lines"""
+    exe = _build(TSAN_STR, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER", "-DELLCUDA_FIN_THREADS=128"], SRC_STR)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-4000:]
+    assert p.stdout.count("step 2: status 1") == 5 and p.stdout.count("step 3: status 0") == 5
+    # sensitivity: the per-tile CTA barrier of the sweep (one warp: __syncwarp, two warps: __syncthreads) was dropped at several
+    # positions and every drop was reported; the barrier after the mbarrier initialisation and the warp's re-convergence at the
+    # end of a tile order no plain memory (no report)
+    assert _races_with_dropped_barrier(exe, 1, "EMU_DROP_SYNCWARP")
+    assert _races_with_dropped_barrier(exe, 1)
