@@ -37,6 +37,8 @@ struct EmuEll {   // the fields of ellcuda_ctx the kernels see (full storage, on
     std::vector<unsigned> counters;
     Scal sc;
     CUtensorMap map;
+    int rank = 0;
+    std::vector<EmuEll*> peers;   // row-sharded group: every rank's handle (this one included), else empty
 };
 
 template <int CO, int R, int ST, int W>
@@ -58,8 +60,9 @@ void run_sweep(EmuEll* h, const double* g, double* plain_out) {   // enqueue_beg
     a.cnt_block = h->counters.data(); a.own_blk = h->xblk.data(); a.out = plain_out;
     a.ld_part = h->ld_part; a.n = h->n; a.w = h->w; a.c_glob0 = h->c0; a.nseg = h->nseg;
     a.exchange = g ? 1 : 0;
-    a.pt.nranks = h->nranks; a.pt.rank = 0;
-    for (int r = 0; r < kMaxRanks; ++r) a.pt.blk[r] = r < h->nranks ? h->xblk.data() : nullptr;
+    a.pt.nranks = h->nranks; a.pt.rank = h->rank;
+    for (int r = 0; r < kMaxRanks; ++r)
+        a.pt.blk[r] = r < h->nranks ? (h->peers.empty() ? h->xblk.data() : h->peers[r]->xblk.data()) : nullptr;
     if (h->cols == 32) sweep_grid<32, 64, 4, 1>(h, a);
     else if (h->cols == 16) sweep_grid<16, 64, 6, 1>(h, a);
     else if (h->tile_rows == 32) sweep_grid<64, 32, 4, 1>(h, a);
@@ -71,10 +74,10 @@ void run_sweep(EmuEll* h, const double* g, double* plain_out) {   // enqueue_beg
 
 // cols: 64 / 32 / 16 (0: alloc_ctx's own choice); tile_rows 64 or 32 (cols = 64 only); warps 1 or 2 (cols = 64, rows = 64 only);
 // ll != 0: grad_t travels as flagged lines through the handle's own exchange block (what an attached rank does), else plain
-extern "C" void* emu_ell_new(long long n, double kappa, const double* mq, const double* diag, const double* xc, int no_defer,
-                             int use_parallel, int reduce_mode, int cols, int tile_rows, int warps, int ll) {
+static EmuEll* new_slab(long long n, long long rb, long long re, double kappa, const double* mq, const double* diag, const double* xc,
+                        int no_defer, int use_parallel, int reduce_mode, int cols, int tile_rows, int warps, int ll) {
     EmuEll* h = new EmuEll();
-    h->n = n; h->w = n; h->c0 = 0;
+    h->n = n; h->w = re - rb; h->c0 = rb;
     h->reduce_mode = reduce_mode; h->nseg = reduce_mode > 0 ? reduce_mode : 1;
     h->no_defer = no_defer; h->use_parallel = use_parallel; h->nranks = ll ? 1 : 0; h->order = 0;
     h->tile_rows = kRowsDefault; h->stages = kStagesDefault; h->warps = warps == 2 ? 2 : 1;
@@ -98,11 +101,78 @@ extern "C" void* emu_ell_new(long long n, double kappa, const double* mq, const 
     h->counters.assign((size_t)(h->ncb + 2), 0u);
     emu_make_map(&h->map, h->S.data(), n, h->w, h->ld, h->tile_rows, h->cols);
     // ---- ellcuda_create: the matrix (symmetric starts only here), the scalars
-    for (long long i = 0; i < n; ++i)
-        for (long long j = 0; j < n; ++j) h->S[(size_t)i * h->ld + j] = mq ? mq[i * n + j] : (i == j ? (diag ? diag[i] : 1.0) : 0.0);
+    for (long long i = 0; i < n; ++i)      // the slab keeps columns [c0, c0 + w) of the (symmetric) matrix: S[i][c] = M[i][c0 + c]
+        for (long long c = 0; c < h->w; ++c) {
+            const long long j = h->c0 + c;
+            h->S[(size_t)i * h->ld + c] = mq ? mq[i * n + j] : (i == j ? (diag ? diag[i] : 1.0) : 0.0);
+        }
     std::memset(&h->sc, 0, sizeof h->sc);
     h->sc.kappa = kappa; h->sc.scale = 1.0; h->sc.epoch = 1;
     return h;
+}
+
+extern "C" void* emu_ell_new(long long n, double kappa, const double* mq, const double* diag, const double* xc, int no_defer,
+                             int use_parallel, int reduce_mode, int cols, int tile_rows, int warps, int ll) {
+    return new_slab(n, 0, n, kappa, mq, diag, xc, no_defer, use_parallel, reduce_mode, cols, tile_rows, warps, ll);
+}
+
+// ---- a row-sharded group in one process: rank r owns rows [r*n/P, (r+1)*n/P) (ellcuda_create with row_begin / row_end +
+// ellcuda_exchange_attach_ptrs).  Every rank's sweep stores its slab of grad_t as flagged lines into EVERY rank's exchange
+// block; every rank's finish polls its own block and derives the same scalars.  The ranks' kernels run one after the other.
+struct EmuGroup {
+    std::vector<EmuEll*> ranks;
+};
+extern "C" void* emu_group_new(int nranks, long long n, double kappa, const double* mq, const double* diag, const double* xc, int no_defer,
+                               int use_parallel, int reduce_mode, int cols) {
+    EmuGroup* g = new EmuGroup();
+    for (int r = 0; r < nranks; ++r)
+        g->ranks.push_back(new_slab(n, n * r / nranks, n * (r + 1) / nranks, kappa, mq, diag, xc, no_defer, use_parallel, reduce_mode, cols, 64, 1, 1));
+    for (int r = 0; r < nranks; ++r) {
+        g->ranks[r]->nranks = nranks;
+        g->ranks[r]->rank = r;
+        g->ranks[r]->peers = g->ranks;
+    }
+    return g;
+}
+static int finish_one(EmuEll* h, int which, const Cut& cut);
+extern "C" int emu_group_update(void* gp, int which, const double* grad, double beta0, int has_beta1, double beta1) {
+    EmuGroup* g = static_cast<EmuGroup*>(gp);
+    const Cut cut = has_beta1 > 0 ? parallel_cut(beta0, beta1) : single_cut(beta0);
+    for (EmuEll* h : g->ranks) {
+        std::copy(grad, grad + h->n, h->gpad.begin());
+        run_sweep(h, h->gpad.data(), nullptr);
+    }
+    int status = -1;
+    for (EmuEll* h : g->ranks) {
+        const int st = finish_one(h, which, cut);
+        if (status >= 0 && st != status) return -100;    // the ranks must agree
+        status = st;
+    }
+    return status;
+}
+// returns 0 when xc, kappa and tsq are identical on every rank (they must be), and rank 0's copy; mq = the slabs side by side
+extern "C" int emu_group_state(void* gp, double* xc, double* mq, double* kappa, double* tsq) {
+    EmuGroup* g = static_cast<EmuGroup*>(gp);
+    int differ = 0;
+    for (EmuEll* h : g->ranks) {
+        run_sweep(h, nullptr, nullptr);                  // flush_pending
+        h->sc.pending = 0; h->sc.scale = 1.0;
+        for (long long i = 0; i < h->n; ++i)
+            for (long long c = 0; c < h->w; ++c) mq[i * h->n + h->c0 + c] = h->S[(size_t)i * h->ld + c];
+        const EmuEll* h0 = g->ranks[0];
+        if (std::memcmp(h->xc.data(), h0->xc.data(), (size_t)h->n * 8) != 0 || std::memcmp(&h->sc.kappa, &h0->sc.kappa, 8) != 0 ||
+            std::memcmp(&h->sc.tsq, &h0->sc.tsq, 8) != 0)
+            differ = 1;
+    }
+    std::copy(g->ranks[0]->xc.begin(), g->ranks[0]->xc.end(), xc);
+    *kappa = g->ranks[0]->sc.kappa;
+    *tsq = g->ranks[0]->sc.tsq;
+    return differ;
+}
+extern "C" void emu_group_free(void* gp) {
+    EmuGroup* g = static_cast<EmuGroup*>(gp);
+    for (EmuEll* h : g->ranks) delete h;
+    delete g;
 }
 
 // ellcuda_update_begin + ellcuda_update_finish; returns the CutStatus
@@ -110,8 +180,11 @@ extern "C" int emu_ell_update(void* hp, int which, const double* g, double beta0
     EmuEll* h = static_cast<EmuEll*>(hp);
     std::copy(g, g + h->n, h->gpad.begin());                      // the padded copy of the gradient (copy_pad_kernel)
     run_sweep(h, h->gpad.data(), nullptr);
-    const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
     const Cut cut = has_beta1 > 0 ? parallel_cut(beta0, beta1) : single_cut(beta0);
+    return finish_one(h, which, cut);
+}
+static int finish_one(EmuEll* h, int which, const Cut& cut) {      // ellcuda_update_finish
+    const CalcConsts cc = CalcConsts::make((int)h->n, h->use_parallel);
     long long fin_ctas = (h->n + kFinThreads - 1) / kFinThreads;
     if (fin_ctas > 16) fin_ctas = 16;
     for (unsigned b = 0; b < (unsigned)fin_ctas; ++b)

@@ -475,6 +475,13 @@ def emu_stream():
     lib.emu_ell_state.argtypes = [C.c_void_p] * 5
     lib.emu_ell_dot_mv.argtypes = [C.c_void_p] * 3
     lib.emu_ell_free.argtypes = [C.c_void_p]
+    lib.emu_group_new.restype = C.c_void_p
+    lib.emu_group_new.argtypes = [C.c_int, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4
+    lib.emu_group_update.restype = C.c_int
+    lib.emu_group_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_double]
+    lib.emu_group_state.restype = C.c_int
+    lib.emu_group_state.argtypes = [C.c_void_p] * 5
+    lib.emu_group_free.argtypes = [C.c_void_p]
     return lib
 
 
@@ -517,6 +524,41 @@ def test_emulated_large_n_update_equals_checker(ref, emu_stream, n, reduce_mode,
         for j in range(n):                                # out[i] = sum_j M[i][j] x[j], j ascending from 0.0 (src/arr.rs:426-442)
             y = y + m[:, j] * x[j]
         assert np.array_equal(e.dot_mv(x), y)
+
+
+@pytest.mark.parametrize("nranks,n,reduce_mode,cols,no_defer", [(2, 130, 0, 64, False), (4, 200, 0, 0, True), (3, 150, 3, 64, False),
+                                                                  (8, 192, 0, 16, False), (2, 100, 2, 32, True)])
+def test_emulated_row_sharded_group_equals_checker(ref, emu_stream, nranks, n, reduce_mode, cols, no_defer):
+    """the multi-GPU form of the large-n path with the real kernels and no GPU: rank r keeps rows [r n/P, (r+1) n/P) of
+    M, every sweep stores its slab of grad_t as flagged lines into every rank's exchange block (epoch-parity double buffer),
+    every finish polls its own block; all ranks must end up with identical xc / kappa / tsq — and with the checker's"""
+    from ellalgo_rs_b200 import _abi as A
+    rng = np.random.default_rng(10 * n + nranks)
+    xc = rng.uniform(-1, 1, n)
+    a = rng.uniform(-1, 1, (n, n)) / n
+    mq = np.ascontiguousarray(np.eye(n) + a + a.T)
+    g = emu_stream.emu_group_new(nranks, n, 1.5, mq.ctypes.data, None, np.ascontiguousarray(xc).ctypes.data, int(no_defer), 1, reduce_mode, cols)
+    s = ref.Space(A.KIND_ELL, n, kappa=1.5, mq=mq, xc=xc, no_defer_trick=no_defer)
+    try:
+        cuts = [(A.UPDATE_BIAS, 0.01, 0.10, False), (A.UPDATE_CENTRAL, 0.0, None, True), (A.UPDATE_BIAS, 1e6, None, True),
+                (A.UPDATE_BIAS, 0.02, None, True), (A.UPDATE_CENTRAL, 0.0, 0.05, False)]
+        for k, (which, b0, b1, single) in enumerate(cuts):
+            grad = np.ascontiguousarray(rng.uniform(-1, 1, n) / np.sqrt(n))
+            st = emu_stream.emu_group_update(g, which, grad.ctypes.data, float(b0), 1 if b1 is not None else (-1 if single else 0),
+                                             0.0 if b1 is None else float(b1))
+            assert st == s.update(which, grad, b0, b1, single), f"step {k}: status (or the ranks disagree)"
+        gx, gm = np.zeros(n), np.zeros((n, n))
+        gk, gt = C.c_double(), C.c_double()
+        assert emu_stream.emu_group_state(g, gx.ctypes.data, gm.ctypes.data, C.byref(gk), C.byref(gt)) == 0, "ranks hold different xc / kappa / tsq"
+        want = s.state()
+        if reduce_mode == 0:
+            assert gt.value == want["tsq"] and gk.value == want["kappa"]
+            assert np.array_equal(gx, want["xc"]) and np.array_equal(gm, want["mq"])
+        else:
+            assert np.allclose([gt.value, gk.value], [want["tsq"], want["kappa"]], rtol=1e-9)
+            assert np.allclose(gx, want["xc"], rtol=1e-9, atol=1e-12) and np.allclose(gm, want["mq"], rtol=1e-9, atol=1e-12)
+    finally:
+        emu_stream.emu_group_free(g)
 
 
 def test_large_n_kernels_no_data_race_under_thread_sanitizer():
