@@ -46,9 +46,6 @@ struct SymArgs {
     int rank, count;       // sharded: this launch covers the pairs rank, rank + count, ... (whole: 0, 1)
 };
 
-__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
 
 struct SymRing {
     unsigned char *tiles, *pends, *gss;
@@ -192,7 +189,7 @@ __global__ void __launch_bounds__(64) sym_sweep_kernel(const __grid_constant__ C
     // prologue (may overlap the preceding finish kernel, see stream_update.cu): barriers and the first tiles of M
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSymStages; ++s) mbar_init(&ring.bars[s], 2);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
         for (int t = 0; t < pre; ++t) {
             int I, J;
             ch.tile_of(t, I, J);
@@ -247,7 +244,7 @@ __device__ __forceinline__ double sym_partial(const double* __restrict__ colpart
 
 __global__ void __launch_bounds__(kCombThreads) sym_combine_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
                                                                    double* __restrict__ out, long long n, long long npad, int nseg) {
-    __shared__ double parts[8 * 32];
+    ELL_STATIC_SHARED double parts[8 * 32];
     pdl_trigger();
     pdl_wait();
     const double s = sym_partial(colpart, rowpart, n, npad, nseg, parts);
@@ -265,7 +262,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(kCombThreads) sym_combine_push_kernel(const double* __restrict__ colpart, const double* __restrict__ rowpart,
                                                                         long long n, long long npad, int nseg, PeerTable pt, Scal* sc,
                                                                         long long slice) {
-    __shared__ double parts[8 * 32];
+    ELL_STATIC_SHARED double parts[8 * 32];
     pdl_trigger();
     pdl_wait();
     const double s = sym_partial(colpart, rowpart, n, npad, nseg, parts, (int)(npad >> 6), pt.rank, pt.nranks);
@@ -289,7 +286,7 @@ __device__ __forceinline__ void sym_reduce_one(long long n, const PeerTable& pt,
     for (int r = 0; r < kMaxRanks; ++r)
         if (r < pt.nranks) {
             const uint4* line = xblk_parts(pt.blk[pt.rank], n, par, pt.nranks, r, slice) + j;
-            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wds[r][0]), "=r"(wds[r][1]), "=r"(wds[r][2]), "=r"(wds[r][3]) : "l"(line) : "memory");
+            ll_peek(line, wds[r]);
         }
     double t = 0.0;
 #pragma unroll
@@ -333,6 +330,7 @@ __global__ void sym_unpack_kernel(const double* __restrict__ Mp, double* __restr
 
 }  // namespace
 
+#ifdef __CUDACC__   // host side: left out when tests/cpp/emu_sym.cpp compiles the kernels of this file for the host
 int sym_alloc(ellcuda_ctx* h) {
     h->T = (h->n + kTile - 1) / kTile;
     const long long npad = h->T * kTile;
@@ -478,5 +476,7 @@ int sym_copy(ellcuda_ctx* dst, const ellcuda_ctx* src, cudaStream_t s) {
     ELL_CUDA_TRY(cudaMemcpyAsync(dst->Mp, src->Mp, tiles * kTileBytes, cudaMemcpyDeviceToDevice, s));
     return ELLCUDA_OK;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace ellcuda
