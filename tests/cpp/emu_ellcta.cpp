@@ -137,7 +137,7 @@ int main() {
         const double kappa40 = 40.0;
         ell_batch_desc d{};
         d.kind = ELL_KIND_ELL; d.oracle_id = ELL_ORACLE_LOWPASS; d.mode = ELL_MODE_OPTIM;
-        d.max_iters = 900; d.tolerance = 1e-14; d.use_parallel_cut = 1;
+        d.max_iters = 500; d.tolerance = 1e-14; d.use_parallel_cut = 1;
         d.kappa0 = &kappa40; d.xc0 = xc0.data(); d.gamma0 = gamma0.data(); d.gamma0_stride = 1;
         d.params = params.data(); d.params_stride = 5; d.params_width = 5;
         d.table = table.data(); d.table_len = (int64_t)table.size(); d.aux[0] = mdim;

@@ -78,6 +78,7 @@ inline void bulk_load_1d(void* dst, const void* src, unsigned bytes, void* bar) 
     std::memcpy(dst, src, bytes);
     mb_update(bar, 0, -(long long)bytes);
 }
+inline void bulk_store_1d(void* dst, const void* src, unsigned bytes) { std::memcpy(dst, src, bytes); }
 inline void bulk_commit() {}
 template <int N>
 inline void bulk_wait_read() {}

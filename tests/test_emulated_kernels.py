@@ -34,6 +34,8 @@ SRC_LP = os.path.join(CPP, "emu_lowpass32.cpp")
 SRC_E64 = os.path.join(CPP, "emu_ell64.cpp")
 SRC_SM = os.path.join(CPP, "emu_batch_small.cpp")
 SRC_STR = os.path.join(CPP, "emu_stream.cpp")
+SRC_SYM = os.path.join(CPP, "emu_sym.cpp")
+LIB_SYM, TSAN_SYM = os.path.join(BUILD, "libemu_sym.so"), os.path.join(BUILD, "emu_sym_tsan")
 LIB_STR, TSAN_STR = os.path.join(BUILD, "libemu_stream.so"), os.path.join(BUILD, "emu_stream_tsan")
 LIB_SM = os.path.join(BUILD, "libemu_batch_small.so")
 LIB_E64, TSAN_E64 = os.path.join(BUILD, "libemu_ell64.so"), os.path.join(BUILD, "emu_ell64_tsan")
@@ -44,7 +46,8 @@ LIB, TSAN = os.path.join(BUILD, "libemu_ellcta.so"), os.path.join(BUILD, "emu_el
 LIB_ST, TSAN_ST = os.path.join(BUILD, "libemu_stable_large.so"), os.path.join(BUILD, "emu_stable_large_tsan")
 DEPS = [os.path.join(CPP, "cuda_emu.h"), os.path.join(CPP, "tmem_emu.h"), os.path.join(CSRC, "batch_lowpass.cu"),
         os.path.join(CSRC, "batch_ell64.cu"), os.path.join(CSRC, "batch_small.cu"), os.path.join(CSRC, "glibc_math.cuh"),
-        os.path.join(CPP, "stream_ptx_emu.h"), os.path.join(CSRC, "stream_update.cu"), os.path.join(CSRC, "stream_common.cuh")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "batch_warp.cu",
+        os.path.join(CPP, "stream_ptx_emu.h"), os.path.join(CSRC, "stream_update.cu"), os.path.join(CSRC, "stream_common.cuh"),
+        os.path.join(CSRC, "stream_sym.cu")] + [os.path.join(CSRC, f) for f in ("ellcta_device.cuh", "stable_large_device.cuh", "batch_warp.cu",
                                                                               "batch_stable.cu", "lmi_device.cuh", "common.cuh",
                                                                               "ell_calc.cuh")]
 
@@ -572,3 +575,57 @@ def test_large_n_kernels_no_data_race_under_thread_sanitizer():
     # end of a tile order no plain memory (no report)
     assert _races_with_dropped_barrier(exe, 1, "EMU_DROP_SYNCWARP")
     assert _races_with_dropped_barrier(exe, 1)
+
+
+# ------------------------------------------------------------------------------------------ large n, symmetric storage
+@pytest.mark.parametrize("nranks,n,start,use_map,no_defer,reduce_mode", [(1, 130, "scalar", 1, False, 0), (1, 200, "dense", 1, True, 0),
+                                                                          (1, 100, "diag", 0, False, 2), (2, 200, "dense", 1, False, 0),
+                                                                          (3, 260, "diag", 1, True, 0), (4, 330, "dense", 0, False, 0)])
+def test_emulated_symmetric_storage_equals_checker(ref, nranks, n, start, use_map, no_defer, reduce_mode):
+    """ELL_STORAGE_SYMMETRIC through sym_sweep / sym_combine (one handle) or sym_combine_push / sym_reduce (sharded by
+    shard_rank / shard_count) + finish_kernel: within 1e-9 of the checker — the bar the device path is held to — and identical
+    on every rank of a group"""
+    from ellalgo_rs_b200 import _abi as A
+    lib = C.CDLL(_build(LIB_SYM, ["-O2", "-fPIC", "-shared"], SRC_SYM))
+    lib.emu_sym_new.restype = C.c_void_p
+    lib.emu_sym_new.argtypes = [C.c_int, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4
+    lib.emu_sym_update.restype = C.c_int
+    lib.emu_sym_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_double]
+    lib.emu_sym_state.restype = C.c_int
+    lib.emu_sym_state.argtypes = [C.c_void_p] * 5
+    lib.emu_sym_free.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(7 * n + nranks)
+    xc = np.ascontiguousarray(rng.uniform(-1, 1, n))
+    kappa, mq, diag = 2.5, None, None
+    if start == "diag":
+        kappa, diag = 1.0, np.ascontiguousarray(rng.uniform(0.5, 2.0, n))
+    elif start == "dense":
+        a = rng.uniform(-1, 1, (n, n)) / n
+        kappa, mq = 1.5, np.ascontiguousarray(np.eye(n) + a + a.T)
+    g = lib.emu_sym_new(nranks, n, kappa, None if mq is None else mq.ctypes.data, None if diag is None else diag.ctypes.data, xc.ctypes.data,
+                        int(no_defer), 1, reduce_mode, use_map)
+    s = ref.Space(A.KIND_ELL, n, kappa=kappa, mq=mq, diag=diag, xc=xc, no_defer_trick=no_defer)
+    try:
+        cuts = [(A.UPDATE_BIAS, 0.01, 0.10, False), (A.UPDATE_CENTRAL, 0.0, None, True), (A.UPDATE_BIAS, 1e6, None, True),
+                (A.UPDATE_BIAS, 0.02, None, True), (A.UPDATE_CENTRAL, 0.0, 0.05, False)]
+        for k, (which, b0, b1, single) in enumerate(cuts):
+            grad = np.ascontiguousarray(rng.uniform(-1, 1, n) / np.sqrt(n))
+            st = lib.emu_sym_update(g, which, grad.ctypes.data, float(b0), 1 if b1 is not None else (-1 if single else 0), 0.0 if b1 is None else float(b1))
+            assert st == s.update(which, grad, b0, b1, single), f"step {k}: status (or the ranks disagree)"
+        gx, gm = np.zeros(n), np.zeros((n, n))
+        gk, gt = C.c_double(), C.c_double()
+        assert lib.emu_sym_state(g, gx.ctypes.data, gm.ctypes.data, C.byref(gk), C.byref(gt)) == 0, "ranks hold different xc / kappa / tsq"
+        want = s.state()
+        assert np.allclose([gt.value, gk.value], [want["tsq"], want["kappa"]], rtol=1e-9)
+        assert np.allclose(gx, want["xc"], rtol=1e-9, atol=1e-12) and np.allclose(gm, want["mq"], rtol=1e-9, atol=1e-12)
+    finally:
+        lib.emu_sym_free(g)
+
+
+def test_symmetric_storage_kernels_no_data_race_under_thread_sanitizer():
+    """two warps share a tile between the passes (CTA barriers), eight warps share the ordered combine's partial sums"""
+    exe = _build(TSAN_SYM, ["-O1", "-fsanitize=thread", "-DEMU_MAIN", "-DEMU_JITTER", "-DELLCUDA_FIN_THREADS=128"], SRC_SYM)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-4000:]
+    assert p.stdout.count("step 1: status 1") == 3 and p.stdout.count("step 2: status 0") == 3 and p.stdout.count("ranks differ 0") == 3
+    assert _races_with_dropped_barrier(exe, 3)       # sensitivity: a CTA barrier of the tile loop
