@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(32 * kW) sweep_kernel(const __grid_constant__ 
 // scalars back, so no CTA can observe a half-updated state.  With peer exchange grad_t is read from this rank's flagged
 // lines (polling until every slab has arrived), otherwise from the plain buffer the sweep (or the caller's allgather) filled.
 #ifndef ELLCUDA_FIN_THREADS
-#define ELLCUDA_FIN_THREADS 1024   // the host emulation under ThreadSanitizer builds with 128 (it tracks <= 256 running threads);
-                                   // the fixed tree of reduce_mode > 0 below is written for the 32 warps of 1024 threads
+#define ELLCUDA_FIN_THREADS 1024   // the host emulation under ThreadSanitizer builds with 128 (it tracks <= 256 running threads)
 #endif
 constexpr int kFinThreads = ELLCUDA_FIN_THREADS;
 constexpr int kFinChunk = 4096;  // products staged per pass (32 KB of shared memory)
@@ -336,7 +335,7 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const double* __res
         if ((tid & 31) == 0) prod[tid >> 5] = acc;
         __syncthreads();
         if (tid < 32) {
-            double v = prod[tid];
+            double v = tid < kFinThreads / 32 ? prod[tid] : 0.0;   // (all 32 entries exist with the device's 1024 threads)
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             if (tid == 0) s_omega = v;

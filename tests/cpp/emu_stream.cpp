@@ -8,10 +8,8 @@
 // for column-block widths 64 / 32 / 16, one or two warps per CTA, row segments, no_defer_trick, dense symmetric starts, failing
 // cuts, with and without the flagged-line exchange; and the hand-offs (mbarrier phases, the CTA-wide staging of the ordered
 // sum) are race-free under ThreadSanitizer.  Test infrastructure only.
-// finish_kernel keeps the device's 1024 threads in the plain build.  The ThreadSanitizer build passes
-// -DELLCUDA_FIN_THREADS=128 (the sanitizer follows <= 256 running threads exactly); the fixed-tree sum of reduce_mode > 0
-// assumes 32 warps and then reads 28 entries of `prod` nobody wrote in that launch, which is why that build's driver runs
-// its reduce_mode > 0 handles first, while the static array is still zero.
+// finish_kernel keeps the device's 1024 threads (and with them the device's summation tree in reduce_mode > 0) in the plain
+// build; the ThreadSanitizer build passes -DELLCUDA_FIN_THREADS=128 (the sanitizer follows <= 256 running threads exactly).
 #include "cuda_emu.h"
 #include "stream_ptx_emu.h"
 
