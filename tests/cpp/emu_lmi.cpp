@@ -101,7 +101,7 @@ int main() {
     const double kappa100 = 100.0;
     ell_batch_desc d{};
     d.kind = ELL_KIND_ELLSTABLE; d.mode = ELL_MODE_FEAS;
-    d.max_iters = 300; d.tolerance = 1e-20; d.use_parallel_cut = 1;
+    d.max_iters = 150; d.tolerance = 1e-20; d.use_parallel_cut = 1;
     d.kappa0 = &kappa100; d.xc0 = xc0.data(); d.xc0_stride = n;
     d.table = table.data(); d.table_len = (int64_t)table.size(); d.aux[0] = m;
     d.oracle_id = ELL_ORACLE_LMI;
